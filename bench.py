@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the full SPH + shape-matching + monodomain step (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 8m|1m|32m|<nx>x<ny>x<nz>]
+
+A "step" is one Animation() of the whole particle set: neighbour search (hash, radix sort, cell table, reorder),
+shape matching (moments, polar decomposition, goal positions), both neighbour passes, ionic model, integration.
+Default workload: BASELINE.json configs[3], the synthetic 8M-particle elongated lattice (512x125x125) with quadratic
+shape matching — the configuration the north_star's throughput target is quoted on; it fits one B200 and is
+strong-scaled over 2/4/8 GPUs (slabs along x).  Inputs are synthetic (lattice generator of the reference's init_cube
+rule) and far larger than L2 (8M x 68 B of persistent state = 544 MB vs 126 MB), so no L2 flush is needed between
+timed steps.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events around exactly K steps, max over
+ranks); `e2e` = the same metric through the C-ABI with HOST buffers: every step uploads the per-particle stimulation
+array from pinned host memory (the per-step control input of this path) and downloads the positions (what the
+reference's viewer reads through Get_Paticles() every frame).  `roofline` is the dominant kernel (fused pass B) from
+CUDA events on the handle's stream; `cpu_baseline` is the reference's own CPU step timed on this box (1 thread — the
+reference has no threading) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec (full SPH+SM+monodomain step)"
+UNIT = "particle-steps/s"
+# algorithmic bytes per particle — whole fused-minimal step and the fused pass B
+STEP_BYTES_PER_PARTICLE = 244
+PASS_B_BYTES_PER_PARTICLE = 92
+PASS_B_NAME = "pass_b(cell+force+laplacian+integrate)"
+
+WORKLOADS = {
+    "1m": dict(dims=(100, 100, 100), quadratic=False, name="synthetic 1M-particle cubic lattice, linear shape matching (configs[2])"),
+    "8m": dict(dims=(512, 125, 125), quadratic=True, name="synthetic 8M-particle elongated lattice 512x125x125, quadratic shape matching (configs[3])"),
+    "32m": dict(dims=(800, 200, 200), quadratic=False, name="synthetic 32M-particle lattice 800x200x200, monodomain pacing (configs[4])"),
+}
+CPU_SAMPLE_DIMS = (40, 40, 40)  # bounded sample for the CPU legs: 64k particles of the same lattice / SM mode
+
+
+def parse_workload(s):
+    if s in WORKLOADS:
+        return dict(WORKLOADS[s], key=s)
+    nx, ny, nz = (int(v) for v in s.lower().split("x"))
+    return dict(dims=(nx, ny, nz), quadratic=False, name=f"synthetic {nx}x{ny}x{nz} lattice, linear shape matching", key=s)
+
+
+def make_lattice(dims):
+    from sph_sm_monodomain_b200 import inputs
+
+    pos, world = inputs.lattice(*dims)
+    fixed, stim = inputs.lattice_masks(pos, dims[0], 8)
+    return pos, world, fixed.astype(np.uint8), np.where(stim, np.float32(300.0), np.float32(0.0)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(quadratic, steps, warmup, backend=None):
+    """The reference's CPU step on this box: genuine class (oracle/_ref, built with its Makefile's -Ofast) when the
+    prebuilt library travelled, else the bit-identical C restatement.  One thread: the reference has no threading."""
+    from oracle import CpuSim, available_backends
+
+    avail = available_backends()
+    if backend is None:
+        backend = "ref_ofast" if "ref_ofast" in avail else ("ref" if "ref" in avail else "port")
+    pos, world, fixed, stim = make_lattice(CPU_SAMPLE_DIMS)
+    sim = CpuSim(backend, capacity=len(pos), world=world)
+    sim.Init_Fluid(pos)
+    sim.set_fields(fixed=fixed, stim=stim)
+    if quadratic:
+        sim.flip_quadratic()
+    sim.Animation(max(warmup, 1))
+    t0 = time.perf_counter()
+    sim.Animation(steps)
+    dt = time.perf_counter() - t0
+    kind = "reference" if backend.startswith("ref") else "port"
+    flags = {"ref_ofast": "g++ -Ofast (the reference Makefile's flags)", "ref": "g++ -O2 -ffp-contract=off", "port": "gcc -O2 -ffp-contract=off"}[backend]
+    d = CPU_SAMPLE_DIMS
+    return {"value": len(pos) * steps / dt, "unit": UNIT, "cores": 1, "kind": kind, "host_cores_available": os.cpu_count(),
+            "sample": f"{d[0]}x{d[1]}x{d[2]} = {len(pos)}-particle lattice of the same spacing and shape-matching mode, {steps} steps, "
+                      f"{flags}, 1 thread (the reference is single-threaded)", "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args, wl, rank, world_size):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 200))
+    base = cpu_reference_rate(wl["quadratic"], steps, min(args.warmup, 3))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 3), "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "sample": base["sample"]},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args, wl, rank, world_size, local_rank):
+    import torch
+
+    from sph_sm_monodomain_b200 import Sim, _capi
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the step has no CPU fallback")
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = local_rank
+    pos, world, fixed, stim = make_lattice(wl["dims"])
+    n_total = len(pos)
+    if world_size > 1:
+        raise SystemExit("multi-GPU slab layer not built yet")
+    sim = Sim(capacity=n_total, world=world, device=device, diagnostics=False)
+    sim.Init_Fluid(pos)
+    sim.set_masks(fixed, stim)
+    if wl["quadratic"]:
+        sim.flip_quadratic()
+    n_local = sim.n
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        sim.sync()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -----------------------------------------------------------------------------
+    sim.Animation(args.warmup)
+    barrier()
+    sim.reset_launch_count()
+    sampler = ClockSampler(device)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    sim.Animation(args.steps)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ev_ms = sim.last_step_ms()
+    clocks = sampler.stop()
+    launches = sim.launch_count()
+    t = torch.tensor([ev_ms, wall_ms], dtype=torch.float64, device=f"cuda:{device}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ev_ms, wall_ms = float(t[0]), float(t[1])
+    value = n_total * args.steps / (ev_ms * 1e-3)
+
+    # ---- per-kernel-group device times (CUDA events on the handle's stream) -> roofline of the dominant kernel -----
+    prof_steps = max(3, min(args.steps, 10))
+    groups = sim.profile_step(prof_steps)
+    peak, peak_src = measured_peak_gbs()
+    pb_ms = groups[PASS_B_NAME]
+    achieved = PASS_B_BYTES_PER_PARTICLE * n_local / (pb_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_pass_b (fused cell model + force + Laplacian + integration)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": PASS_B_BYTES_PER_PARTICLE, "ms_per_launch": pb_ms,
+                "whole_step": {"achieved": STEP_BYTES_PER_PARTICLE * n_total / (ev_ms / args.steps * 1e-3) / 1e9,
+                               "algorithmic_bytes_per_particle": STEP_BYTES_PER_PARTICLE},
+                "kernel_group_ms": groups}
+    roofline["whole_step"]["frac"] = roofline["whole_step"]["achieved"] / peak
+    traffic_file = os.path.join(ROOT, "profiles", "pass_b_traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as fh:
+            tr = json.load(fh)
+        if tr.get("workload") == wl["key"]:
+            roofline["traffic"] = tr.get("dram_bytes_per_launch")
+
+    # ---- end to end through the C-ABI with host buffers ---------------------------------------------------------------
+    stim_host = torch.from_numpy(stim.copy()).pin_memory()
+    pos_host = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
+    lib = sim.lib
+    FP = C.POINTER(C.c_float)
+    stim_ptr = C.cast(stim_host.data_ptr(), FP)
+    pos_ptr = C.cast(pos_host.data_ptr(), FP)
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        _capi.check(lib, sim.h, lib.sphsm_set_masks(sim.h, None, stim_ptr, n_local))    # H2D: 4 B / particle
+        _capi.check(lib, sim.h, lib.sphsm_step(sim.h, 1))
+        _capi.check(lib, sim.h, lib.sphsm_download_positions(sim.h, pos_ptr, n_local))  # D2H: 12 B / particle
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{device}")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": n_total * e2e_steps / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(4 * n_total),
+           "d2h_bytes_per_step": int(12 * n_total), "steps": e2e_steps,
+           "protocol": "per step: sphsm_set_masks(stim) from pinned host memory -> sphsm_step(1) -> sphsm_download_positions to pinned host memory"}
+    assert np.isfinite(pos_host.numpy()).all()
+
+    if rank == 0:
+        cpu = cpu_reference_rate(wl["quadratic"], 20, 2) if not args.no_cpu_baseline else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": wl["name"], "particles": n_total, "world": [round(w, 4) for w in world],
+                           "shape_matching": "quadratic" if wl["quadratic"] else "linear", "parallelism": f"slab{world_size}",
+                           "l2": "inputs larger than L2 (no flush): %.0f MB of persistent state" % (n_total * 68 / 1e6)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
+                "roofline": roofline}
+        if cpu:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores_available")}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="8m")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = parse_workload(args.workload)
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world_size)
+    else:
+        run_ours(args, wl, rank, world_size, local_rank)
+
+
+if __name__ == "__main__":
+    main()

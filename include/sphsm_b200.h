@@ -1,0 +1,191 @@
+/* sphsm_b200.h — the C-ABI of libsphsm_b200.so: the B200 (sm_100a) implementation of the
+ * SPH_SM_monodomain per-timestep particle pipeline.
+ *
+ * This is the ONLY boundary between host code and CUDA: the drop-in C++ class in
+ * include/SPH_SM_monodomain.h, the ctypes binding in sph_sm_monodomain_b200/_capi.py, the tests and
+ * bench.py all call exactly these entry points; nothing else touches the device.  Plain pointers and
+ * sizes, no C++/torch types.  Each entry point cites the reference interface it replaces ("h" =
+ * SPH_SM_monodomain/SPH_SM_monodomain.h, "cpp" = SPH_SM_monodomain/SPH_SM_monodomain.cpp of
+ * Hagen23/SPH-SM-Monodomain).
+ *
+ * Conventions: every function returns 0 (SPHSM_OK) or a negative sphsm_status and never throws or aborts
+ * across the ABI; sphsm_last_error() gives the message of the last failure on that handle (or of the last
+ * failed sphsm_create when h == NULL).  A handle owns its device memory, stream and CUDA graph; calls are
+ * asynchronous on the handle's stream except download / get_* / sync, which synchronise.  One host thread
+ * per handle.  There is NO CPU fallback: without a usable CUDA device sphsm_create fails with
+ * SPHSM_ERR_CUDA.
+ */
+#ifndef SPHSM_B200_H
+#define SPHSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHSM_ABI_VERSION 1
+
+typedef enum {
+    SPHSM_OK = 0,
+    SPHSM_ERR_INVALID = -1,  /* bad argument / bad state */
+    SPHSM_ERR_CUDA = -2,     /* CUDA runtime error (message in sphsm_last_error) */
+    SPHSM_ERR_CAPACITY = -3, /* more particles than params.capacity */
+    SPHSM_ERR_COMM = -4      /* NCCL / multi-GPU error */
+} sphsm_status;
+
+/* Stage ids: the call order of compute_SPH_SM_monodomain, cpp:794-824. */
+typedef enum {
+    SPHSM_STAGE_STEP = 0,                   /* Animation(), cpp:826-829 */
+    SPHSM_STAGE_FIND_NEIGHBORS = 1,         /* Find_neighbors, cpp:199-213 */
+    SPHSM_STAGE_CORRECTED_VELOCITY = 2,     /* calculate_corrected_velocity, cpp:653-667 (+215-446) */
+    SPHSM_STAGE_INTERMEDIATE_VELOCITY = 3,  /* calculate_intermediate_velocity, cpp:669-701 */
+    SPHSM_STAGE_DENSITY_PRESSURE = 4,       /* Compute_Density_SingPressure, cpp:448-513 */
+    SPHSM_STAGE_CELL_MODEL = 5,             /* calculate_cell_model, cpp:575-593 */
+    SPHSM_STAGE_FORCE = 6,                  /* Compute_Force, cpp:515-573 */
+    SPHSM_STAGE_UPDATE = 7                  /* Update_Properties, cpp:598-651 */
+} sphsm_stage_id;
+
+/* Every tunable the reference hard-codes in its ctor (cpp:13-69) or in-class initialisers (h:72-94).
+ * sphsm_default_params() fills in the reference's values bit-for-bit. */
+typedef struct {
+    uint32_t struct_size;   /* = sizeof(sphsm_params); checked by sphsm_create */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t capacity;       /* Max_Number_Paticles, cpp:19 (50000) */
+    float world[3];         /* World_Size, cpp:29 (1.5,1.5,1.5); also the SM bounds max, cpp:61 */
+    float kernel_h;         /* kernel == Cell_Size, cpp:17,31 (0.04f) */
+    float gravity[3];       /* cpp:39 */
+    float K;                /* cpp:40 */
+    float stand_density;    /* cpp:41 */
+    float time_delta;       /* cpp:47 */
+    float wall_hit;         /* cpp:48 */
+    float mu;               /* cpp:49 */
+    float velocity_mixing;  /* cpp:43 */
+    float poly6_constant;   /* cpp:54 */
+    float spiky_constant;   /* cpp:55 */
+    float bspline_constant; /* cpp:57 */
+    float alpha, beta;      /* cpp:64-65 */
+    int32_t quadratic_match;     /* cpp:67 */
+    int32_t volume_conservation; /* cpp:68 */
+    int32_t allow_flip;          /* cpp:69 */
+    float Cm, Beta, sigma;  /* cpp:23-26 */
+    float stim_strength;    /* cpp:27 */
+    float FH_Vt, FH_Vp, FH_Vr, C1, C2, C3, C4; /* h:72-80 */
+    float voltage_constant, max_pressure, max_voltage; /* h:92-94 */
+    float particle_mass;    /* Init_Particle, cpp:116 (0.2f) */
+    /* --- implementation controls (no reference counterpart) --- */
+    int32_t diagnostics;    /* 1: every step also materialises the reference's intermediate Particle fields
+                               (predicted_vel, goal, corrected_vel, inter_vel, acc, pres, Inter_Vm) so that
+                               sphsm_download_aos returns all 33 fields exactly as Get_Paticles() would show
+                               them; 0: only persistent state is kept current (fused fast path). */
+    int32_t strict;         /* 1: reference-order arithmetic (no FMA contraction, sequential float moment sums,
+                               double where the reference promotes) for bit-level validation at small N;
+                               0: the production path. */
+    int32_t slab_axis;      /* multi-GPU: axis (0,1,2) the domain is cut along; also the slowest-varying axis of
+                               the internal cell key. -1: single-GPU reference key order (x fastest). */
+    int32_t reserved[8];
+} sphsm_params;
+
+typedef struct sphsm_handle sphsm_handle;
+
+/* Same field order/size/padding as the reference's `Particle` (Particle.h:7-35): 132 bytes. */
+#define SPHSM_PARTICLE_STRIDE 132
+
+int sphsm_abi_version(void);
+
+/* ctor defaults, cpp:13-79 + h:72-94.  world/capacity may then be changed before sphsm_create (the derived
+ * Grid_Size / Number_Cells, cpp:32-37, follow from world and kernel_h). */
+int sphsm_default_params(sphsm_params *p);
+
+/* SPH_SM_monodomain::SPH_SM_monodomain() / ~SPH_SM_monodomain(), cpp:13-85 */
+int sphsm_create(const sphsm_params *p, sphsm_handle **out);
+int sphsm_destroy(sphsm_handle *h);
+
+/* Live parameter changes: add_viscosity (cpp:87-91), flip_quadratic / flip_volume (h:154-155), the public
+ * voltage_constant / max_pressure / max_voltage (h:92-94).  world, kernel_h, capacity, device are fixed at create. */
+int sphsm_get_params(sphsm_handle *h, sphsm_params *out);
+int sphsm_set_params(sphsm_handle *h, const sphsm_params *p);
+
+/* Init_Fluid(std::vector<m3Vector>) / Init_Particle, cpp:93-125: APPENDS n particles (pos = orig = goal,
+ * vel = 0, dens = Stand_Density, mass = particle_mass, Vm = Iion = stim = w = 0); particles beyond capacity are
+ * silently dropped exactly as cpp:103 does (the return value stays SPHSM_OK). xyz: n*3 floats. */
+int sphsm_init_fluid(sphsm_handle *h, const float *xyz, int n);
+
+/* Whole-array state exchange with the caller's Particle[] (Get_Paticles(), h:150).  `stride` is the byte
+ * distance between consecutive particles (SPHSM_PARTICLE_STRIDE for the reference layout).  upload replaces the
+ * simulation state with n particles; download writes all 33 fields of the first n particles in the caller's
+ * (original) particle order. */
+int sphsm_upload_aos(sphsm_handle *h, const void *particles, int n, int stride);
+int sphsm_download_aos(sphsm_handle *h, void *particles, int n, int stride);
+/* pos (3 floats per particle, original order) only — what main.cpp's display_points reads every frame. */
+int sphsm_download_positions(sphsm_handle *h, float *xyz, int n);
+
+/* set_stim(center, radius, strength), cpp:704-717 — NB squared distance is compared with `radius`. */
+int sphsm_set_stim(sphsm_handle *h, float cx, float cy, float cz, float radius, float strength);
+/* turnOnStim_Mesh / turnOnStim_Cube, cpp:745-762 / 719-743 (one fused device pass over positions x particles
+ * instead of the reference's per-position set_stim loop; same result). xyz: n*3 floats. */
+int sphsm_stim_mesh(sphsm_handle *h, const float *xyz, int n);
+int sphsm_stim_cube(sphsm_handle *h, const float *xyz, int n);
+/* turnOffStim, cpp:764-783 */
+int sphsm_stim_off(sphsm_handle *h);
+/* Overwrite the per-particle fixed flags / stimulation values (original particle order, n entries each; either
+ * pointer may be NULL).  The reference's callers do this by writing through Get_Paticles(). */
+int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const float *stim, int n);
+
+/* Animation() x nsteps, cpp:826-829 */
+int sphsm_step(sphsm_handle *h, int nsteps);
+/* One stage of the step (the reference exposes them as public methods, h:120-143).  Stages 3, 4 and 6 rebuild
+ * the neighbour grid first if the particle data changed since it was last built. */
+int sphsm_stage(sphsm_handle *h, int stage);
+int sphsm_sync(sphsm_handle *h);
+
+int sphsm_num_particles(sphsm_handle *h);  /* Get_Particle_Number, h:148 */
+int sphsm_num_cells(sphsm_handle *h);      /* Number_Cells, cpp:37 */
+int sphsm_grid_size(sphsm_handle *h, int out3[3]); /* Grid_Size, cpp:32-35 */
+int sphsm_total_time_steps(sphsm_handle *h);       /* total_time_steps, h:101 */
+
+/* Accumulated device time (seconds) of the seven stages in the order of the d_* members (h:99):
+ * find_neighbors, corrected_velocity, intermediate_velocity, Density_SingPressure, cell_model, compute_Force,
+ * Update_Properties.  Only filled while stage timing is enabled (it serialises the step with CUDA events). */
+int sphsm_enable_stage_timing(sphsm_handle *h, int on);
+int sphsm_get_stage_times(sphsm_handle *h, double out7[7]);
+
+/* Buckets after Find_neighbors as CSR in the REFERENCE's hash order (cpp:136-146): cell_start has
+ * sphsm_num_cells()+1 entries, indices has sphsm_num_particles() entries of original particle indices
+ * (ascending inside a bucket, as the reference's push_back order yields). */
+int sphsm_get_cells_csr(sphsm_handle *h, int *cell_start, int *indices);
+/* Neighbour sets computed ON THE DEVICE by the same traversal the passes use, for the first n_query original
+ * particle indices in `query`: kind 0 = candidate set (27 cells); 1 = {r2 <= h*h} (Poly6); 2 = {r2 > 1e-12 &&
+ * r <= h} (Spiky/Visco); 3 = {r2 > 1e-12 && r/h < 2} (B_spline_2).  counts[n_query]; indices[n_query*cap] holds
+ * original particle indices sorted ascending. */
+int sphsm_get_neighbor_sets(sphsm_handle *h, int kind, const int *query, int n_query, int cap, int *counts, int *indices);
+
+/* Shape-matching internals of the last calculate_corrected_velocity: cm[3], original cm[3], and the transform
+ * (27 floats: the linear T in [0..8], or the quadratic 3x9 matrix). */
+int sphsm_get_sm_transform(sphsm_handle *h, float cm[3], float ocm[3], float xform[27]);
+
+/* Counters for bench.py: kernels launched by this handle since creation / since the last reset. */
+int sphsm_get_launch_count(sphsm_handle *h, long long *launches);
+int sphsm_reset_launch_count(sphsm_handle *h);
+/* Device time (ms, CUDA events on the handle's stream) of the last sphsm_step call's nsteps steps in total. */
+int sphsm_last_step_ms(sphsm_handle *h, float *ms);
+/* Average device time (ms per launch) of each kernel group inside the last profiled step, see bench.py. */
+#define SPHSM_NUM_KERNEL_GROUPS 8
+int sphsm_profile_step(sphsm_handle *h, int nsteps, float out_ms[SPHSM_NUM_KERNEL_GROUPS]);
+const char *sphsm_kernel_group_name(int group);
+
+/* ---- multi-GPU (one process per GPU; slab decomposition along params.slab_axis) ------------------------- */
+/* NCCL bootstrap: rank 0 calls sphsm_comm_unique_id (128 bytes) and shares it by any means (bench.py uses
+ * torch.distributed); every rank then calls sphsm_comm_init on its own handle. */
+int sphsm_comm_unique_id(void *id128);
+int sphsm_comm_init(sphsm_handle *h, int nranks, int rank, const void *id128);
+/* Slab of this rank in cell planes [lo, hi) along slab_axis; particles outside are dropped at upload. */
+int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi);
+
+const char *sphsm_last_error(sphsm_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHSM_B200_H */

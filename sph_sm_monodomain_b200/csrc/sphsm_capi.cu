@@ -1,0 +1,992 @@
+// sphsm_capi.cu — libsphsm_b200.so: handle, step orchestration and the extern "C" entry points declared in
+// include/sphsm_b200.h.  All device work is in the hand-written sm_100a kernels of sphsm_{sort,sm,pass}.cuh;
+// there is no CPU fallback anywhere in this file.
+#include "../../include/sphsm_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "sphsm_pass.cuh"
+#include "sphsm_sm.cuh"
+#include "sphsm_sort.cuh"
+#include "sphsm_types.cuh"
+
+using namespace sphsm;
+
+// byte offsets inside the reference's Particle (Particle.h:10-29)
+enum : int {
+    OFF_POS = 0, OFF_VEL = 12, OFF_PVEL = 24, OFF_IVEL = 36, OFF_CVEL = 48, OFF_ACC = 60, OFF_MASS = 72, OFF_ORIG = 76,
+    OFF_GOAL = 88, OFF_FIXED = 100, OFF_DENS = 104, OFF_PRES = 108, OFF_VM = 112, OFF_IVM = 116, OFF_IION = 120,
+    OFF_STIM = 124, OFF_W = 128
+};
+
+static std::string g_create_error;
+
+enum KernelGroup { KG_HASH = 0, KG_SORT, KG_GRID, KG_MOMENTS, KG_GOAL, KG_PASS_A, KG_PASS_B, KG_OTHER };
+static const char *kGroupNames[SPHSM_NUM_KERNEL_GROUPS] = {"hash", "radix_sort", "cell_bounds+reorder", "sm_moments+solve",
+                                                           "goal+corrected_vel", "pass_a(density+xsph)",
+                                                           "pass_b(cell+force+laplacian+integrate)", "other"};
+
+struct sphsm_handle {
+    sphsm_params prm;
+    DevParams dp;
+    int n = 0;
+    cudaStream_t stream = nullptr;
+    Arrays cur{}, alt{};
+    uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    uint32_t *ghist = nullptr, *tile_state = nullptr, *tile_counter = nullptr;
+    int sorted_buf = 0;  // which keys[] / vals[] hold the sorted result
+    int *cell_start = nullptr, *slot_of = nullptr;
+    SmState *sm = nullptr;
+    double *partial = nullptr, *totals = nullptr;
+    float *scratch = nullptr;
+    uint8_t *d_aos = nullptr;
+    size_t aos_cap_bytes = 0;
+    float *d_tmp = nullptr;  // staging for position lists (stim_mesh / stim_cube / init_fluid)
+    size_t tmp_cap = 0;
+    int *d_itmp = nullptr;
+    size_t itmp_cap = 0;
+    bool grid_valid = false, rest_dirty = true, inter_live = true, slot_of_valid = false;
+    int sort_passes = 1, max_tiles = 1, red_blocks = 1;
+    long long launches = 0;
+    int total_steps = 0;
+    bool stage_timing = false;
+    double stage_time[7] = {0, 0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[SPHSM_NUM_KERNEL_GROUPS + 2] = {};
+    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
+    float last_step_ms = 0.f;
+    bool profiling = false;
+    float group_ms[SPHSM_NUM_KERNEL_GROUPS] = {};
+    int group_launches[SPHSM_NUM_KERNEL_GROUPS] = {};
+    std::string err;
+};
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            if (h) h->err = b_; else g_create_error = b_;                                          \
+            return SPHSM_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+#define LAUNCH(kern, grid, block, ...)                       \
+    do {                                                     \
+        kern<<<(grid), (block), 0, h->stream>>>(__VA_ARGS__); \
+        h->launches++;                                       \
+    } while (0)
+
+static int fail(sphsm_handle *h, int code, const char *msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------------
+// defaults: the reference ctor, cpp:13-69, with its float/double promotions
+extern "C" int sphsm_abi_version(void) { return SPHSM_ABI_VERSION; }
+
+extern "C" int sphsm_default_params(sphsm_params *p) {
+    if (!p) return SPHSM_ERR_INVALID;
+    memset(p, 0, sizeof(*p));
+    p->struct_size = (uint32_t)sizeof(*p);
+    p->device = 0;
+    p->capacity = 50000;
+    p->world[0] = p->world[1] = p->world[2] = 1.5f;
+    p->kernel_h = 0.04f;
+    p->gravity[0] = 0.0f; p->gravity[1] = -9.8f; p->gravity[2] = 0.0f;
+    p->K = 0.5f;
+    p->stand_density = 1112.0f;
+    const float max_vel2 = 3.0f * 3.0f + 3.0f * 3.0f + 3.0f * 3.0f;                          // max_vel.magnitudeSquared()
+    p->time_delta = (float)(0.4 * (double)p->kernel_h / (double)sqrtf(max_vel2));            // cpp:47
+    p->wall_hit = -1.0f;
+    p->mu = 100.0f;
+    p->velocity_mixing = 1.0f;
+    const float pi = 3.1415926535897932f;                                                    // m3Pi, m3Real.h:9
+    p->poly6_constant = (float)((double)315.0f / ((double)(64.0f * pi) * pow((double)p->kernel_h, 9.0)));  // cpp:54
+    p->spiky_constant = (float)((double)45.0f / ((double)pi * pow((double)p->kernel_h, 6.0)));             // cpp:55
+    p->bspline_constant = 1.0f / (pi * p->kernel_h * p->kernel_h * p->kernel_h);                           // cpp:57
+    p->alpha = 0.3f; p->beta = 0.4f;
+    p->quadratic_match = 0; p->volume_conservation = 1; p->allow_flip = 0;
+    p->Cm = 1.f; p->Beta = 50;
+    {
+        float sigma_i = 0.893, sigma_e = 0.67;  // cpp:15 (double literals narrowed to float)
+        p->sigma = sigma_i * sigma_e / (sigma_i + sigma_e);
+    }
+    p->stim_strength = 300.0f;
+    p->FH_Vt = -75.0; p->FH_Vp = 15.0; p->FH_Vr = -85.0;
+    p->C1 = 0.175; p->C2 = 0.03; p->C3 = 0.011; p->C4 = 0.55;
+    p->voltage_constant = 1; p->max_pressure = 15000; p->max_voltage = 200;
+    p->particle_mass = 0.2f;
+    p->diagnostics = 1;
+    p->strict = 0;
+    p->slab_axis = -1;
+    return SPHSM_OK;
+}
+
+// largest float x (searching around `guess`) with pred(x) true, pred monotone (true below, false above)
+template <class Pred>
+static float max_float_where(Pred pred, float guess) {
+    float x = guess;
+    while (!pred(x)) x = nextafterf(x, 0.0f);
+    while (pred(nextafterf(x, INFINITY))) x = nextafterf(x, INFINITY);
+    return x;
+}
+
+static void derive_dev_params(sphsm_handle *h) {
+    const sphsm_params &q = h->prm;
+    DevParams &d = h->dp;
+    memset(&d, 0, sizeof d);
+    d.n = h->n;
+    d.cell_size = q.kernel_h;  // Cell_Size == kernel, cpp:17,31
+    d.h = q.kernel_h;
+    d.h2 = q.kernel_h * q.kernel_h;
+    for (int a = 0; a < 3; a++) {
+        d.world[a] = q.world[a];
+        d.gravity[a] = q.gravity[a];
+        d.g[a] = (int)ceilf(q.world[a] / d.cell_size);  // cpp:32-35
+    }
+    if (q.slab_axis >= 0 && q.slab_axis <= 2) {
+        d.perm[2] = q.slab_axis;
+        d.perm[0] = (q.slab_axis + 1) % 3;
+        d.perm[1] = (q.slab_axis + 2) % 3;
+        if (d.perm[0] > d.perm[1]) std::swap(d.perm[0], d.perm[1]);
+    } else {
+        d.perm[0] = 0; d.perm[1] = 1; d.perm[2] = 2;
+    }
+    d.ga = d.g[d.perm[0]]; d.gb = d.g[d.perm[1]]; d.gc = d.g[d.perm[2]];
+    d.c_off = 0; d.gcl = d.gc; d.slab_lo = 0; d.slab_hi = d.gc;
+    d.num_cells = d.ga * d.gb * d.gcl;
+    d.K = q.K; d.rho0 = q.stand_density; d.dt = q.time_delta; d.inv_dt = 1.0f / q.time_delta;  // cpp:661
+    d.wall_hit = q.wall_hit; d.mu = q.mu; d.mix = q.velocity_mixing;
+    d.c_poly6 = q.poly6_constant; d.c_spiky = q.spiky_constant; d.c_bspline = q.bspline_constant;
+    d.alpha = q.alpha; d.beta = q.beta;
+    d.quadratic = q.quadratic_match; d.volume = q.volume_conservation; d.allow_flip = q.allow_flip;
+    d.Cm = q.Cm; d.Beta = q.Beta; d.sigma = q.sigma;
+    d.diff_coef = q.sigma / (q.Beta * q.Cm);  // cpp:571
+    d.Vr = q.FH_Vr;
+    d.fh_denom = q.FH_Vp - q.FH_Vr;                 // cpp:579
+    d.fh_asd = (q.FH_Vt - q.FH_Vr) / d.fh_denom;    // cpp:580
+    d.C1 = q.C1; d.C2 = q.C2; d.C3 = q.C3; d.C4 = q.C4;
+    d.voltage_constant = q.voltage_constant; d.max_pressure = q.max_pressure; d.max_voltage = q.max_voltage;
+    const float hh = d.h;
+    d.r2_spiky = max_float_where([hh](float x) { return sqrtf(x) <= hh; }, hh * hh);
+    d.r2_q1 = max_float_where([hh](float x) { return (sqrtf(x) / hh) < 1.0f; }, hh * hh);
+    d.r2_q2 = max_float_where([hh](float x) { return (sqrtf(x) / hh) < 2.0f; }, 4.0f * hh * hh);
+    d.bs_a1 = (float)(4.5 * (double)d.c_bspline / (double)hh);
+    d.bs_b1 = (float)(-3.0 * (double)d.c_bspline);
+    d.bs_a2 = (float)(-1.5 * (double)d.c_bspline / (double)hh);
+    d.bs_b2 = (float)(3.0 * (double)d.c_bspline);
+    d.poly6_self = (float)((double)d.c_poly6 * pow((double)(d.h2 - 0.0f), 3.0));  // Poly6(0.0f), cpp:151,483
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int alloc_arrays(sphsm_handle *h, Arrays &a, int cap, bool with_cold) {
+    size_t n4 = (size_t)cap * sizeof(float4);
+    CU(cudaMalloc(&a.P, n4)); CU(cudaMalloc(&a.VEL, n4)); CU(cudaMalloc(&a.O, n4)); CU(cudaMalloc(&a.E, n4));
+    CU(cudaMalloc(&a.ID, (size_t)cap * sizeof(int)));
+    CU(cudaMalloc(&a.C, n4)); CU(cudaMalloc(&a.V, n4)); CU(cudaMalloc(&a.S, (size_t)cap * sizeof(float2)));
+    CU(cudaMalloc(&a.ACC, n4)); CU(cudaMalloc(&a.GOAL, n4)); CU(cudaMalloc(&a.PV, n4));
+    CU(cudaMemset(a.C, 0, n4)); CU(cudaMemset(a.V, 0, n4)); CU(cudaMemset(a.S, 0, (size_t)cap * sizeof(float2)));
+    CU(cudaMemset(a.ACC, 0, n4)); CU(cudaMemset(a.GOAL, 0, n4)); CU(cudaMemset(a.PV, 0, n4));
+    if (with_cold) {
+        CU(cudaMalloc(&a.COLD_GOAL, n4)); CU(cudaMalloc(&a.COLD_PV, n4));
+        CU(cudaMemset(a.COLD_GOAL, 0, n4)); CU(cudaMemset(a.COLD_PV, 0, n4));
+    }
+    return SPHSM_OK;
+}
+static void free_arrays(Arrays &a, bool with_cold) {
+    cudaFree(a.P); cudaFree(a.VEL); cudaFree(a.O); cudaFree(a.E); cudaFree(a.ID); cudaFree(a.C); cudaFree(a.V);
+    cudaFree(a.S); cudaFree(a.ACC); cudaFree(a.GOAL); cudaFree(a.PV);
+    if (with_cold) { cudaFree(a.COLD_GOAL); cudaFree(a.COLD_PV); }
+}
+
+static int setup_grid_buffers(sphsm_handle *h) {
+    // (re)allocates what depends on the number of cells
+    if (h->cell_start) cudaFree(h->cell_start);
+    h->cell_start = nullptr;
+    CU(cudaMalloc(&h->cell_start, ((size_t)h->dp.num_cells + 2) * sizeof(int)));
+    int bits = 1;
+    while ((1ll << bits) < (long long)h->dp.num_cells + 1) bits++;
+    h->sort_passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+    if (h->sort_passes > MAX_SORT_PASSES) return fail(h, SPHSM_ERR_INVALID, "grid too large for the radix sort key");
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
+    sphsm_handle *h = nullptr;
+    if (!p || !out) return fail(nullptr, SPHSM_ERR_INVALID, "null argument");
+    if (p->struct_size != sizeof(sphsm_params)) return fail(nullptr, SPHSM_ERR_INVALID, "sphsm_params.struct_size mismatch (ABI)");
+    if (p->capacity <= 0 || p->kernel_h <= 0.f || p->world[0] <= 0.f || p->world[1] <= 0.f || p->world[2] <= 0.f)
+        return fail(nullptr, SPHSM_ERR_INVALID, "capacity, kernel_h and world must be positive");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (p->device < 0 || p->device >= ndev) return fail(nullptr, SPHSM_ERR_CUDA, "no such CUDA device (no CPU fallback exists)");
+    CU(cudaSetDevice(p->device));
+    sphsm_handle *nh = new sphsm_handle();
+    nh->prm = *p;
+    nh->n = 0;
+    derive_dev_params(nh);
+    {
+        long long cells = (long long)nh->dp.ga * nh->dp.gb * nh->dp.gcl;
+        if (cells <= 0 || cells >= (1ll << 30)) {
+            delete nh;
+            return fail(nullptr, SPHSM_ERR_INVALID, "grid has too many cells");
+        }
+    }
+    h = nh;
+    const int cap = p->capacity;
+    int rc;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if ((rc = alloc_arrays(h, h->cur, cap, true)) != 0) return rc;
+    if ((rc = alloc_arrays(h, h->alt, cap, false)) != 0) return rc;
+    h->alt.COLD_GOAL = h->cur.COLD_GOAL;
+    h->alt.COLD_PV = h->cur.COLD_PV;
+    for (int k = 0; k < 2; k++) {
+        CU(cudaMalloc(&h->keys[k], (size_t)cap * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->vals[k], (size_t)cap * sizeof(uint32_t)));
+    }
+    h->max_tiles = cdiv(cap, SORT_TILE);
+    CU(cudaMalloc(&h->ghist, MAX_SORT_PASSES * RADIX * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->tile_state, (size_t)MAX_SORT_PASSES * h->max_tiles * RADIX * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->tile_counter, MAX_SORT_PASSES * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->slot_of, (size_t)cap * sizeof(int)));
+    CU(cudaMalloc(&h->sm, sizeof(SmState)));
+    CU(cudaMemset(h->sm, 0, sizeof(SmState)));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, p->device));
+    h->red_blocks = std::max(1, std::min(2 * prop.multiProcessorCount, cdiv(cap, 256)));
+    CU(cudaMalloc(&h->partial, (size_t)h->red_blocks * 10 * 9 * sizeof(double)));
+    CU(cudaMalloc(&h->totals, 128 * sizeof(double)));
+    CU(cudaMalloc(&h->scratch, 162 * sizeof(float)));
+    if ((rc = setup_grid_buffers(h)) != 0) return rc;
+    for (auto &e : h->ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreate(&h->ev_step0));
+    CU(cudaEventCreate(&h->ev_step1));
+    *out = h;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_destroy(sphsm_handle *h) {
+    if (!h) return SPHSM_OK;
+    cudaSetDevice(h->prm.device);
+    cudaStreamSynchronize(h->stream);
+    free_arrays(h->cur, true);
+    free_arrays(h->alt, false);
+    for (int k = 0; k < 2; k++) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
+    cudaFree(h->ghist); cudaFree(h->tile_state); cudaFree(h->tile_counter); cudaFree(h->cell_start); cudaFree(h->slot_of);
+    cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
+    cudaFree(h->d_itmp);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->ev_step0) cudaEventDestroy(h->ev_step0);
+    if (h->ev_step1) cudaEventDestroy(h->ev_step1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SPHSM_OK;
+}
+
+extern "C" const char *sphsm_last_error(sphsm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int sphsm_get_params(sphsm_handle *h, sphsm_params *out) {
+    if (!h || !out) return SPHSM_ERR_INVALID;
+    *out = h->prm;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_set_params(sphsm_handle *h, const sphsm_params *p) {
+    if (!h || !p) return SPHSM_ERR_INVALID;
+    if (p->struct_size != sizeof(sphsm_params)) return fail(h, SPHSM_ERR_INVALID, "sphsm_params.struct_size mismatch (ABI)");
+    if (p->capacity != h->prm.capacity || p->device != h->prm.device || p->kernel_h != h->prm.kernel_h ||
+        memcmp(p->world, h->prm.world, sizeof p->world) != 0 || p->slab_axis != h->prm.slab_axis)
+        return fail(h, SPHSM_ERR_INVALID, "capacity, device, kernel_h, world and slab_axis are fixed at create");
+    const int c_off = h->dp.c_off, gcl = h->dp.gcl, lo = h->dp.slab_lo, hi = h->dp.slab_hi, nc = h->dp.num_cells;
+    h->prm = *p;
+    derive_dev_params(h);
+    h->dp.c_off = c_off; h->dp.gcl = gcl; h->dp.slab_lo = lo; h->dp.slab_hi = hi; h->dp.num_cells = nc;
+    return SPHSM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AoS <-> SoA
+__device__ __forceinline__ float ldf(const uint8_t *rec, int off) { return *reinterpret_cast<const float *>(rec + off); }
+__device__ __forceinline__ void stf(uint8_t *rec, int off, float v) { *reinterpret_cast<float *>(rec + off) = v; }
+
+__global__ void k_aos_to_soa(int first, int count, const uint8_t *__restrict__ aos, int stride, Arrays a) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int i = first + k;
+    const uint8_t *r = aos + (size_t)k * stride;
+    const float mass = ldf(r, OFF_MASS), dens = ldf(r, OFF_DENS), Vm = ldf(r, OFF_VM);
+    const int fixed = r[OFF_FIXED] != 0;
+    a.P[i] = make_float4(ldf(r, OFF_POS), ldf(r, OFF_POS + 4), ldf(r, OFF_POS + 8), mass);
+    a.VEL[i] = make_float4(ldf(r, OFF_VEL), ldf(r, OFF_VEL + 4), ldf(r, OFF_VEL + 8), dens);
+    a.O[i] = make_float4(ldf(r, OFF_ORIG), ldf(r, OFF_ORIG + 4), ldf(r, OFF_ORIG + 8), __int_as_float(fixed ? i + 1 : 0));
+    a.E[i] = make_float4(Vm, ldf(r, OFF_IION), ldf(r, OFF_W), ldf(r, OFF_STIM));
+    a.ID[i] = i;
+    a.C[i] = make_float4(ldf(r, OFF_CVEL), ldf(r, OFF_CVEL + 4), ldf(r, OFF_CVEL + 8), __fdiv_rn(mass, dens));
+    a.V[i] = make_float4(ldf(r, OFF_IVEL), ldf(r, OFF_IVEL + 4), ldf(r, OFF_IVEL + 8), __fdiv_rn(mass, dens));
+    a.S[i] = make_float2(ldf(r, OFF_PRES), Vm);
+    a.ACC[i] = make_float4(ldf(r, OFF_ACC), ldf(r, OFF_ACC + 4), ldf(r, OFF_ACC + 8), ldf(r, OFF_IVM));
+    const float4 goal = make_float4(ldf(r, OFF_GOAL), ldf(r, OFF_GOAL + 4), ldf(r, OFF_GOAL + 8), 0.f);
+    const float4 pv = make_float4(ldf(r, OFF_PVEL), ldf(r, OFF_PVEL + 4), ldf(r, OFF_PVEL + 8), 0.f);
+    a.GOAL[i] = goal; a.PV[i] = pv;
+    a.COLD_GOAL[i] = goal; a.COLD_PV[i] = pv;
+}
+
+__global__ void k_soa_to_aos(int n, Arrays a, uint8_t *__restrict__ aos, int stride) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int id = a.ID[s];
+    uint8_t *r = aos + (size_t)id * stride;
+    const float4 p = a.P[s], v = a.VEL[s], o = a.O[s], e = a.E[s], c = a.C[s], iv = a.V[s], acc = a.ACC[s];
+    const float2 sp = a.S[s];
+    const int flags = __float_as_int(o.w);
+    const float4 goal = flags ? a.COLD_GOAL[flags - 1] : a.GOAL[s];
+    const float4 pv = flags ? a.COLD_PV[flags - 1] : a.PV[s];
+    stf(r, OFF_POS, p.x); stf(r, OFF_POS + 4, p.y); stf(r, OFF_POS + 8, p.z);
+    stf(r, OFF_VEL, v.x); stf(r, OFF_VEL + 4, v.y); stf(r, OFF_VEL + 8, v.z);
+    stf(r, OFF_PVEL, pv.x); stf(r, OFF_PVEL + 4, pv.y); stf(r, OFF_PVEL + 8, pv.z);
+    stf(r, OFF_IVEL, iv.x); stf(r, OFF_IVEL + 4, iv.y); stf(r, OFF_IVEL + 8, iv.z);
+    stf(r, OFF_CVEL, c.x); stf(r, OFF_CVEL + 4, c.y); stf(r, OFF_CVEL + 8, c.z);
+    stf(r, OFF_ACC, acc.x); stf(r, OFF_ACC + 4, acc.y); stf(r, OFF_ACC + 8, acc.z);
+    stf(r, OFF_MASS, p.w);
+    stf(r, OFF_ORIG, o.x); stf(r, OFF_ORIG + 4, o.y); stf(r, OFF_ORIG + 8, o.z);
+    stf(r, OFF_GOAL, goal.x); stf(r, OFF_GOAL + 4, goal.y); stf(r, OFF_GOAL + 8, goal.z);
+    r[OFF_FIXED] = flags ? 1 : 0; r[OFF_FIXED + 1] = 0; r[OFF_FIXED + 2] = 0; r[OFF_FIXED + 3] = 0;
+    stf(r, OFF_DENS, v.w); stf(r, OFF_PRES, sp.x); stf(r, OFF_VM, e.x); stf(r, OFF_IVM, acc.w);
+    stf(r, OFF_IION, e.y); stf(r, OFF_STIM, e.w); stf(r, OFF_W, e.z);
+}
+
+__global__ void k_positions_out(int n, Arrays a, float *__restrict__ xyz) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int id = a.ID[s];
+    const float4 p = a.P[s];
+    xyz[3 * (size_t)id] = p.x; xyz[3 * (size_t)id + 1] = p.y; xyz[3 * (size_t)id + 2] = p.z;
+}
+
+// Init_Particle, cpp:101-125
+__global__ void k_init_particles(int first, int count, const float *__restrict__ xyz, Arrays a, float mass, float rho0) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int i = first + k;
+    const float x = xyz[3 * (size_t)k], y = xyz[3 * (size_t)k + 1], z = xyz[3 * (size_t)k + 2];
+    a.P[i] = make_float4(x, y, z, mass);
+    a.VEL[i] = make_float4(0.f, 0.f, 0.f, rho0);
+    a.O[i] = make_float4(x, y, z, __int_as_float(0));
+    a.E[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.ID[i] = i;
+    a.C[i] = make_float4(0.f, 0.f, 0.f, __fdiv_rn(mass, rho0));
+    a.V[i] = make_float4(0.f, 0.f, 0.f, __fdiv_rn(mass, rho0));
+    a.S[i] = make_float2(0.f, 0.f);
+    a.ACC[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.GOAL[i] = make_float4(x, y, z, 0.f);
+    a.PV[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.COLD_GOAL[i] = make_float4(x, y, z, 0.f);
+    a.COLD_PV[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__global__ void k_slot_of(int n, const int *__restrict__ id, int *__restrict__ slot_of) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n) slot_of[id[s]] = s;
+}
+
+// ---- stimulation / fixation ------------------------------------------------------------------------------
+// set_stim (cpp:704-717) for a LIST of centres: stim = strength where the squared distance to any centre <= radius
+__global__ void __launch_bounds__(256) k_set_stim_list(int n, Arrays a, const float *__restrict__ centres, int m, float radius, float strength) {
+    __shared__ float sc[256 * 3];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 p = make_float4(0, 0, 0, 0);
+    if (s < n) p = a.P[s];
+    bool hit = false;
+    for (int base = 0; base < m; base += 256) {
+        const int cnt = min(256, m - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < cnt * 3; k += blockDim.x) sc[k] = centres[(size_t)base * 3 + k];
+        __syncthreads();
+        if (!hit && s < n) {
+            for (int k = 0; k < cnt; k++) {
+                const float dx = __fsub_rn(p.x, sc[3 * k]), dy = __fsub_rn(p.y, sc[3 * k + 1]), dz = __fsub_rn(p.z, sc[3 * k + 2]);
+                if (dist2_exact(dx, dy, dz) <= radius) { hit = true; break; }
+            }
+        }
+        if (__syncthreads_and(hit || s >= n)) break;
+    }
+    if (hit && s < n) a.E[s].w = strength;
+}
+
+// mode 0: turnOnStim_Mesh's fixation rule (cpp:759), 1: turnOnStim_Cube's (cpp:738); comparisons against double
+// literals are done in double exactly as the reference's promotions make them.
+__global__ void k_fix_rule(int n, Arrays a, int mode, int diag) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 p = a.P[s];
+    bool fix;
+    if (mode == 0) {
+        const double x = p.x, y = p.y;
+        fix = (x >= 0.0 && x <= 0.07) || (x >= 0.90 && y >= 0.80);
+    } else {
+        fix = (p.y == 0.0f && p.x <= 0.48f) || (p.y == 0.0f && (double)p.x >= 1.0);
+    }
+    if (fix && __float_as_int(a.O[s].w) == 0) {
+        const int id = a.ID[s];
+        if (diag) { a.COLD_GOAL[id] = a.GOAL[s]; a.COLD_PV[id] = a.PV[s]; }
+        a.O[s].w = __int_as_float(id + 1);
+    }
+}
+
+__global__ void k_set_masks(int n, Arrays a, const uint8_t *__restrict__ fixed, const float *__restrict__ stim, int diag) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int id = a.ID[s];
+    if (fixed) {
+        const int was = __float_as_int(a.O[s].w);
+        if (fixed[id] && !was) {
+            if (diag) { a.COLD_GOAL[id] = a.GOAL[s]; a.COLD_PV[id] = a.PV[s]; }
+            a.O[s].w = __int_as_float(id + 1);
+        } else if (!fixed[id] && was) {
+            a.GOAL[s] = a.COLD_GOAL[was - 1];
+            a.PV[s] = a.COLD_PV[was - 1];
+            a.O[s].w = __int_as_float(0);
+        }
+    }
+    if (stim) a.E[s].w = stim[id];
+}
+
+// turnOffStim, cpp:764-783
+__global__ void k_stim_off(int n, Arrays a) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    a.E[s] = make_float4(0.0f, 0.0f, 0.0f, -10000.0f);  // Vm, Iion, w = 0; stim = -10000
+    a.S[s] = make_float2(-10000.0f, 0.0f);              // pres = -10000
+    a.ACC[s].w = 0.0f;                                  // Inter_Vm = 0
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int ensure_tmp(sphsm_handle *h, size_t floats) {
+    if (h->tmp_cap >= floats) return SPHSM_OK;
+    if (h->d_tmp) cudaFree(h->d_tmp);
+    h->d_tmp = nullptr; h->tmp_cap = 0;
+    CU(cudaMalloc(&h->d_tmp, floats * sizeof(float)));
+    h->tmp_cap = floats;
+    return SPHSM_OK;
+}
+static int ensure_itmp(sphsm_handle *h, size_t ints) {
+    if (h->itmp_cap >= ints) return SPHSM_OK;
+    if (h->d_itmp) cudaFree(h->d_itmp);
+    h->d_itmp = nullptr; h->itmp_cap = 0;
+    CU(cudaMalloc(&h->d_itmp, ints * sizeof(int)));
+    h->itmp_cap = ints;
+    return SPHSM_OK;
+}
+static int ensure_aos(sphsm_handle *h, size_t bytes) {
+    if (h->aos_cap_bytes >= bytes) return SPHSM_OK;
+    if (h->d_aos) cudaFree(h->d_aos);
+    h->d_aos = nullptr; h->aos_cap_bytes = 0;
+    CU(cudaMalloc(&h->d_aos, bytes));
+    h->aos_cap_bytes = bytes;
+    return SPHSM_OK;
+}
+static void state_changed(sphsm_handle *h, bool rest) {
+    h->grid_valid = false;
+    h->slot_of_valid = false;
+    h->inter_live = true;
+    if (rest) h->rest_dirty = true;
+}
+
+extern "C" int sphsm_init_fluid(sphsm_handle *h, const float *xyz, int n) {
+    if (!h || (!xyz && n > 0) || n < 0) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    const int take = std::min(n, h->prm.capacity - h->n);  // cpp:103: the rest is silently dropped
+    if (take <= 0) return SPHSM_OK;
+    int rc;
+    if ((rc = ensure_tmp(h, (size_t)take * 3)) != 0) return rc;
+    CU(cudaMemcpyAsync(h->d_tmp, xyz, (size_t)take * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_init_particles, cdiv(take, 256), 256, h->n, take, h->d_tmp, h->cur, h->prm.particle_mass, h->prm.stand_density);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));  // xyz may be pageable / freed by the caller
+    h->n += take;
+    h->dp.n = h->n;
+    state_changed(h, true);
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_upload_aos(sphsm_handle *h, const void *particles, int n, int stride) {
+    if (!h || !particles || n < 0 || stride < SPHSM_PARTICLE_STRIDE) return SPHSM_ERR_INVALID;
+    if (n > h->prm.capacity) return fail(h, SPHSM_ERR_CAPACITY, "more particles than capacity");
+    CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if ((rc = ensure_aos(h, (size_t)std::max(n, 1) * stride)) != 0) return rc;
+    CU(cudaMemcpyAsync(h->d_aos, particles, (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
+    if (n > 0) LAUNCH(k_aos_to_soa, cdiv(n, 256), 256, 0, n, h->d_aos, stride, h->cur);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    h->n = n;
+    h->dp.n = n;
+    state_changed(h, true);
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_download_aos(sphsm_handle *h, void *particles, int n, int stride) {
+    if (!h || !particles || n < 0 || stride < SPHSM_PARTICLE_STRIDE) return SPHSM_ERR_INVALID;
+    if (n > h->n) return fail(h, SPHSM_ERR_INVALID, "n exceeds the number of particles");
+    CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if ((rc = ensure_aos(h, (size_t)std::max(h->n, 1) * stride)) != 0) return rc;
+    if (stride != SPHSM_PARTICLE_STRIDE)  // keep the caller's padding bytes: round-trip through the device image
+        CU(cudaMemcpyAsync(h->d_aos, particles, (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
+    if (h->n > 0) LAUNCH(k_soa_to_aos, cdiv(h->n, 256), 256, h->n, h->cur, h->d_aos, stride);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(particles, h->d_aos, (size_t)n * stride, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_download_positions(sphsm_handle *h, float *xyz, int n) {
+    if (!h || !xyz || n < 0 || n > h->n) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if ((rc = ensure_tmp(h, (size_t)std::max(h->n, 1) * 3)) != 0) return rc;
+    if (h->n > 0) LAUNCH(k_positions_out, cdiv(h->n, 256), 256, h->n, h->cur, h->d_tmp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(xyz, h->d_tmp, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SPHSM_OK;
+}
+
+static int stim_list(sphsm_handle *h, const float *centres, int m, float radius, float strength) {
+    if (m <= 0 || h->n <= 0) return SPHSM_OK;
+    int rc;
+    if ((rc = ensure_tmp(h, (size_t)m * 3)) != 0) return rc;
+    CU(cudaMemcpyAsync(h->d_tmp, centres, (size_t)m * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_set_stim_list, cdiv(h->n, 256), 256, h->n, h->cur, h->d_tmp, m, radius, strength);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_set_stim(sphsm_handle *h, float cx, float cy, float cz, float radius, float strength) {
+    if (!h) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    const float c[3] = {cx, cy, cz};
+    return stim_list(h, c, 1, radius, strength);
+}
+
+extern "C" int sphsm_stim_mesh(sphsm_handle *h, const float *xyz, int n) {
+    if (!h || (!xyz && n > 0)) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    int rc = stim_list(h, xyz, n, 0.01f, h->prm.stim_strength);  // cpp:753
+    if (rc) return rc;
+    if (h->n > 0) LAUNCH(k_fix_rule, cdiv(h->n, 256), 256, h->n, h->cur, 0, h->prm.diagnostics);
+    CU(cudaGetLastError());
+    h->rest_dirty = true;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_stim_cube(sphsm_handle *h, const float *xyz, int n) {
+    if (!h || (!xyz && n > 0)) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    std::vector<float> sel;
+    for (int i = 0; i < n; i++) {  // the position filter of cpp:727 (double-literal comparisons)
+        const float px = xyz[3 * i], pz = xyz[3 * i + 2];
+        if (((double)px >= 0.45 && (double)px <= 0.48) || ((double)px > 1.0 && pz <= 1.05f)) {
+            sel.push_back(px); sel.push_back(xyz[3 * i + 1]); sel.push_back(pz);
+        }
+    }
+    int rc = stim_list(h, sel.data(), (int)(sel.size() / 3), 0.001f, h->prm.stim_strength);  // cpp:728
+    if (rc) return rc;
+    if (h->n > 0) LAUNCH(k_fix_rule, cdiv(h->n, 256), 256, h->n, h->cur, 1, h->prm.diagnostics);
+    CU(cudaGetLastError());
+    h->rest_dirty = true;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_stim_off(sphsm_handle *h) {
+    if (!h) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    if (h->n > 0) LAUNCH(k_stim_off, cdiv(h->n, 256), 256, h->n, h->cur);
+    CU(cudaGetLastError());
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const float *stim, int n) {
+    if (!h || n != h->n) return fail(h, SPHSM_ERR_INVALID, "set_masks needs exactly num_particles entries");
+    if (n == 0 || (!fixed && !stim)) return SPHSM_OK;
+    CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if ((rc = ensure_tmp(h, (size_t)n)) != 0) return rc;
+    if ((rc = ensure_itmp(h, (size_t)(n + 3) / 4)) != 0) return rc;
+    if (stim) CU(cudaMemcpyAsync(h->d_tmp, stim, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (fixed) CU(cudaMemcpyAsync(h->d_itmp, fixed, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_set_masks, cdiv(n, 256), 256, n, h->cur, fixed ? (const uint8_t *)h->d_itmp : nullptr, stim ? h->d_tmp : nullptr,
+           h->prm.diagnostics);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    if (fixed) h->rest_dirty = true;
+    return SPHSM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the step
+struct GroupTimer {  // records an event at each kernel-group boundary while profiling
+    sphsm_handle *h;
+    int idx = 0;
+    int groups[SPHSM_NUM_KERNEL_GROUPS + 2];
+    long long l0;
+    explicit GroupTimer(sphsm_handle *hh) : h(hh) {
+        l0 = h->launches;
+        if (h->profiling) cudaEventRecord(h->ev[0], h->stream);
+    }
+    void end_group(int g) {
+        if (!h->profiling) return;
+        groups[idx] = g;
+        h->group_launches[g] += (int)(h->launches - l0);
+        l0 = h->launches;
+        idx++;
+        cudaEventRecord(h->ev[idx], h->stream);
+    }
+    void finish() {
+        if (!h->profiling) return;
+        cudaEventSynchronize(h->ev[idx]);
+        for (int k = 0; k < idx; k++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev[k], h->ev[k + 1]);
+            h->group_ms[groups[k]] += ms;
+        }
+    }
+};
+
+static void swap_sets(sphsm_handle *h, bool all) {
+    std::swap(h->cur.P, h->alt.P); std::swap(h->cur.VEL, h->alt.VEL); std::swap(h->cur.O, h->alt.O);
+    std::swap(h->cur.E, h->alt.E); std::swap(h->cur.ID, h->alt.ID);
+    if (all) {
+        std::swap(h->cur.C, h->alt.C); std::swap(h->cur.V, h->alt.V); std::swap(h->cur.S, h->alt.S);
+        std::swap(h->cur.ACC, h->alt.ACC); std::swap(h->cur.GOAL, h->alt.GOAL); std::swap(h->cur.PV, h->alt.PV);
+    }
+}
+
+// Find_neighbors: hash -> radix sort -> cell table -> reorder
+static int build_grid(sphsm_handle *h, GroupTimer *gt) {
+    const int n = h->n;
+    if (n == 0) { h->grid_valid = true; return SPHSM_OK; }
+    const int passes = h->sort_passes;
+    const int tiles = cdiv(n, SORT_TILE);
+    CU(cudaMemsetAsync(h->ghist, 0, MAX_SORT_PASSES * RADIX * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->tile_state, 0, (size_t)passes * tiles * RADIX * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->tile_counter, 0, MAX_SORT_PASSES * sizeof(uint32_t), h->stream));
+    LAUNCH(k_hash, std::min(cdiv(n, 256), 8 * 148), 256, h->dp, h->cur.P, h->keys[0], h->ghist, passes);
+    if (gt) gt->end_group(KG_HASH);
+    int src = 0;
+    for (int k = 0; k < passes; k++) {
+        LAUNCH(k_radix_pass, tiles, SORT_THREADS, h->keys[src], k == 0 ? nullptr : h->vals[src], h->keys[src ^ 1], h->vals[src ^ 1], n,
+               k * RADIX_BITS, h->ghist + k * RADIX, h->tile_state + (size_t)k * tiles * RADIX, h->tile_counter + k);
+        src ^= 1;
+    }
+    h->sorted_buf = src;
+    if (h->prm.strict) LAUNCH(k_cell_order_fix, cdiv(n, 128), 128, h->keys[src], h->vals[src], h->cur.ID, n);
+    if (gt) gt->end_group(KG_SORT);
+    LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
+    const bool all = h->prm.diagnostics || h->inter_live;
+    LAUNCH(k_reorder, cdiv(n, 256), 256, n, h->vals[src], h->cur, h->alt, all ? 1 : 0);
+    swap_sets(h, all);
+    if (gt) gt->end_group(KG_GRID);
+    CU(cudaGetLastError());
+    h->grid_valid = true;
+    h->slot_of_valid = false;
+    return SPHSM_OK;
+}
+
+static int ensure_slot_of(sphsm_handle *h) {
+    if (h->slot_of_valid || h->n == 0) return SPHSM_OK;
+    LAUNCH(k_slot_of, cdiv(h->n, 256), 256, h->n, h->cur.ID, h->slot_of);
+    CU(cudaGetLastError());
+    h->slot_of_valid = true;
+    return SPHSM_OK;
+}
+
+static int rest_moments(sphsm_handle *h) {
+    const int n = h->n, B = h->red_blocks;
+    LAUNCH(k_rest_pass1, B, 256, n, h->cur.P, h->cur.O, h->partial);
+    LAUNCH(k_sum_partials, 1, 256, h->partial, B, 5, h->totals);
+    LAUNCH(k_rest_finalize1, 1, 1, h->totals, h->sm);
+    LAUNCH(k_rest_pass2, dim3(B, 10), 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
+    for (int r = 0; r < 10; r++) LAUNCH(k_sum_partials, 1, 256, h->partial + (size_t)r * B * 9, B, 9, h->totals + r * 9);
+    LAUNCH(k_rest_finalize2, 1, 1, h->totals, h->sm, h->scratch);
+    CU(cudaGetLastError());
+    h->rest_dirty = false;
+    return SPHSM_OK;
+}
+
+// calculate_corrected_velocity
+template <bool STRICT>
+static int corrected_velocity(sphsm_handle *h, bool diag, GroupTimer *gt) {
+    const int n = h->n;
+    if (n == 0) return SPHSM_OK;
+    int rc;
+    if (n > 1) {  // projectPositions returns early for <= 1 particle, cpp:236
+        if (STRICT) {
+            if ((rc = ensure_slot_of(h)) != 0) return rc;
+            LAUNCH(k_sm_strict, 1, 1, h->dp, h->cur.P, h->cur.O, h->slot_of, h->sm, h->scratch);
+        } else {
+            if (h->rest_dirty && (rc = rest_moments(h)) != 0) return rc;
+            const int B = h->red_blocks;
+            if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
+            else LAUNCH(k_moments<3>, B, 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
+            LAUNCH(k_sum_partials, 1, 256, h->partial, B, h->dp.quadratic ? 33 : 15, h->totals);
+            LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
+        }
+    }
+    if (gt) gt->end_group(KG_MOMENTS);
+    const int keep_goal = n <= 1;  // projectPositions returned early: mGoalPos keeps its previous value
+    if (diag || keep_goal) LAUNCH((k_goal_cvel<STRICT, true>), cdiv(n, 256), 256, h->dp, h->cur, h->sm, keep_goal);
+    else LAUNCH((k_goal_cvel<STRICT, false>), cdiv(n, 256), 256, h->dp, h->cur, h->sm, 0);
+    if (gt) gt->end_group(KG_GOAL);
+    CU(cudaGetLastError());
+    return SPHSM_OK;
+}
+
+template <bool STRICT>
+static int run_stage(sphsm_handle *h, int stage) {
+    const int n = h->n;
+    int rc;
+    if (n == 0) return SPHSM_OK;
+    if ((stage == 3 || stage == 4 || stage == 6) && !h->grid_valid && (rc = build_grid(h, nullptr)) != 0) return rc;
+    switch (stage) {
+        case SPHSM_STAGE_FIND_NEIGHBORS:
+            return build_grid(h, nullptr);
+        case SPHSM_STAGE_CORRECTED_VELOCITY:
+            return corrected_velocity<STRICT>(h, true, nullptr);
+        case SPHSM_STAGE_INTERMEDIATE_VELOCITY:
+            LAUNCH(k_refresh_derived, cdiv(n, 256), 256, n, h->cur, 1, 0);
+            LAUNCH((k_pass_a<STRICT, false, true>), cdiv(n, 128), 128, h->dp, h->cur, h->cell_start);
+            break;
+        case SPHSM_STAGE_DENSITY_PRESSURE:
+            LAUNCH((k_pass_a<STRICT, true, false>), cdiv(n, 128), 128, h->dp, h->cur, h->cell_start);
+            break;
+        case SPHSM_STAGE_CELL_MODEL:
+            LAUNCH(k_cell_model<STRICT>, cdiv(n, 256), 256, h->dp, h->cur);
+            break;
+        case SPHSM_STAGE_FORCE:
+            LAUNCH(k_refresh_derived, cdiv(n, 256), 256, n, h->cur, 0, 1);
+            LAUNCH((k_pass_b<STRICT, PB_FORCE_ONLY>), cdiv(n, 128), 128, h->dp, h->cur, (float4 *)nullptr, h->cell_start);
+            break;
+        case SPHSM_STAGE_UPDATE:
+            LAUNCH(k_update<STRICT>, cdiv(n, 256), 256, h->dp, h->cur);
+            h->grid_valid = false;
+            break;
+        default:
+            return fail(h, SPHSM_ERR_INVALID, "unknown stage id");
+    }
+    CU(cudaGetLastError());
+    return SPHSM_OK;
+}
+
+// one fused step: grid, shape matching, pass A, pass B
+template <bool STRICT>
+static int fused_step(sphsm_handle *h) {
+    const int n = h->n;
+    int rc;
+    if (n == 0) return SPHSM_OK;
+    const bool diag = h->prm.diagnostics != 0;
+    GroupTimer gt(h);
+    if ((rc = build_grid(h, &gt)) != 0) return rc;
+    if ((rc = corrected_velocity<STRICT>(h, diag, &gt)) != 0) return rc;
+    LAUNCH((k_pass_a<STRICT, true, true>), cdiv(n, 128), 128, h->dp, h->cur, h->cell_start);
+    gt.end_group(KG_PASS_A);
+    if (diag) LAUNCH((k_pass_b<STRICT, PB_FUSED_DIAG>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
+    else LAUNCH((k_pass_b<STRICT, PB_FUSED>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
+    std::swap(h->cur.P, h->alt.P);
+    gt.end_group(KG_PASS_B);
+    CU(cudaGetLastError());
+    gt.finish();
+    h->grid_valid = false;
+    h->inter_live = false;
+    return SPHSM_OK;
+}
+
+// the staged step with an event pair around every stage (what the class's d_* timers report)
+template <bool STRICT>
+static int timed_staged_step(sphsm_handle *h) {
+    for (int st = 1; st <= 7; st++) {
+        CU(cudaEventRecord(h->ev[0], h->stream));
+        int rc = run_stage<STRICT>(h, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->ev[1], h->stream));
+        CU(cudaEventSynchronize(h->ev[1]));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        h->stage_time[st - 1] += ms * 1e-3;
+    }
+    h->inter_live = false;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_step(sphsm_handle *h, int nsteps) {
+    if (!h || nsteps < 0) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    CU(cudaEventRecord(h->ev_step0, h->stream));
+    for (int s = 0; s < nsteps; s++) {
+        int rc;
+        if (h->stage_timing) rc = h->prm.strict ? timed_staged_step<true>(h) : timed_staged_step<false>(h);
+        else rc = h->prm.strict ? fused_step<true>(h) : fused_step<false>(h);
+        if (rc) return rc;
+        h->total_steps++;
+    }
+    CU(cudaEventRecord(h->ev_step1, h->stream));
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_stage(sphsm_handle *h, int stage) {
+    if (!h) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    if (stage == SPHSM_STAGE_STEP) return sphsm_step(h, 1);
+    h->inter_live = true;
+    return h->prm.strict ? run_stage<true>(h, stage) : run_stage<false>(h, stage);
+}
+
+extern "C" int sphsm_sync(sphsm_handle *h) {
+    if (!h) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_last_step_ms(sphsm_handle *h, float *ms) {
+    if (!h || !ms) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    CU(cudaEventSynchronize(h->ev_step1));
+    CU(cudaEventElapsedTime(ms, h->ev_step0, h->ev_step1));
+    h->last_step_ms = *ms;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_profile_step(sphsm_handle *h, int nsteps, float out_ms[SPHSM_NUM_KERNEL_GROUPS]) {
+    if (!h || !out_ms || nsteps <= 0) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    for (int g = 0; g < SPHSM_NUM_KERNEL_GROUPS; g++) { h->group_ms[g] = 0.f; h->group_launches[g] = 0; }
+    h->profiling = true;
+    int rc = SPHSM_OK;
+    for (int s = 0; s < nsteps && rc == SPHSM_OK; s++) {
+        rc = h->prm.strict ? fused_step<true>(h) : fused_step<false>(h);
+        if (rc == SPHSM_OK) h->total_steps++;
+    }
+    h->profiling = false;
+    for (int g = 0; g < SPHSM_NUM_KERNEL_GROUPS; g++) out_ms[g] = h->group_ms[g] / (float)nsteps;
+    return rc;
+}
+
+extern "C" const char *sphsm_kernel_group_name(int g) { return (g >= 0 && g < SPHSM_NUM_KERNEL_GROUPS) ? kGroupNames[g] : ""; }
+
+extern "C" int sphsm_num_particles(sphsm_handle *h) { return h ? h->n : SPHSM_ERR_INVALID; }
+extern "C" int sphsm_num_cells(sphsm_handle *h) { return h ? h->dp.g[0] * h->dp.g[1] * h->dp.g[2] : SPHSM_ERR_INVALID; }
+extern "C" int sphsm_grid_size(sphsm_handle *h, int out3[3]) {
+    if (!h || !out3) return SPHSM_ERR_INVALID;
+    for (int a = 0; a < 3; a++) out3[a] = h->dp.g[a];
+    return SPHSM_OK;
+}
+extern "C" int sphsm_total_time_steps(sphsm_handle *h) { return h ? h->total_steps : SPHSM_ERR_INVALID; }
+
+extern "C" int sphsm_enable_stage_timing(sphsm_handle *h, int on) {
+    if (!h) return SPHSM_ERR_INVALID;
+    h->stage_timing = on != 0;
+    return SPHSM_OK;
+}
+extern "C" int sphsm_get_stage_times(sphsm_handle *h, double out7[7]) {
+    if (!h || !out7) return SPHSM_ERR_INVALID;
+    for (int k = 0; k < 7; k++) out7[k] = h->stage_time[k];
+    return SPHSM_OK;
+}
+extern "C" int sphsm_get_launch_count(sphsm_handle *h, long long *launches) {
+    if (!h || !launches) return SPHSM_ERR_INVALID;
+    *launches = h->launches;
+    return SPHSM_OK;
+}
+extern "C" int sphsm_reset_launch_count(sphsm_handle *h) {
+    if (!h) return SPHSM_ERR_INVALID;
+    h->launches = 0;
+    return SPHSM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inspection
+extern "C" int sphsm_get_cells_csr(sphsm_handle *h, int *cell_start, int *indices) {
+    if (!h || !cell_start || !indices) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if (!h->grid_valid && (rc = build_grid(h, nullptr)) != 0) return rc;
+    const DevParams &d = h->dp;
+    const int n = h->n, ncell = d.g[0] * d.g[1] * d.g[2];
+    std::vector<uint32_t> keys(std::max(n, 1));
+    std::vector<int> ids(std::max(n, 1));
+    CU(cudaMemcpyAsync(keys.data(), h->keys[h->sorted_buf], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(ids.data(), h->cur.ID, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    // internal key -> the reference's hash x + Gx*(y + Gy*z) (cpp:142); stable counting sort keeps slot order
+    std::vector<int> ref_hash(n);
+    std::fill(cell_start, cell_start + ncell + 1, 0);
+    for (int s = 0; s < n; s++) {
+        const uint32_t k = keys[s];
+        if ((int)k >= d.num_cells) { ref_hash[s] = -1; continue; }
+        int c[3];
+        c[d.perm[0]] = (int)(k % d.ga);
+        c[d.perm[1]] = (int)((k / d.ga) % d.gb);
+        c[d.perm[2]] = (int)(k / ((uint32_t)d.ga * d.gb)) + d.c_off;
+        ref_hash[s] = c[0] + d.g[0] * (c[1] + d.g[1] * c[2]);
+        cell_start[ref_hash[s] + 1]++;
+    }
+    for (int c = 0; c < ncell; c++) cell_start[c + 1] += cell_start[c];
+    std::vector<int> cursor(cell_start, cell_start + ncell);
+    for (int s = 0; s < n; s++)
+        if (ref_hash[s] >= 0) indices[cursor[ref_hash[s]]++] = ids[s];
+    // the reference's bucket order is ascending particle index
+    for (int c = 0; c < ncell; c++) std::sort(indices + cell_start[c], indices + cell_start[c + 1]);
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_get_neighbor_sets(sphsm_handle *h, int kind, const int *query, int n_query, int cap, int *counts, int *indices) {
+    if (!h || !query || !counts || !indices || n_query < 0 || cap <= 0 || kind < 0 || kind > 3) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    for (int i = 0; i < n_query; i++)
+        if (query[i] < 0 || query[i] >= h->n) return fail(h, SPHSM_ERR_INVALID, "query index out of range");
+    if (n_query == 0) return SPHSM_OK;
+    int rc;
+    if (!h->grid_valid && (rc = build_grid(h, nullptr)) != 0) return rc;
+    if ((rc = ensure_slot_of(h)) != 0) return rc;
+    if ((rc = ensure_itmp(h, (size_t)n_query * (2 + (size_t)cap))) != 0) return rc;
+    int *d_query = h->d_itmp, *d_counts = h->d_itmp + n_query, *d_idx = h->d_itmp + 2 * (size_t)n_query;
+    CU(cudaMemcpyAsync(d_query, query, (size_t)n_query * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(k_neighbor_sets, cdiv(n_query, 64), 64, h->dp, h->cur, h->cell_start, h->slot_of, d_query, n_query, kind, cap, d_counts, d_idx);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts, d_counts, (size_t)n_query * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(indices, d_idx, (size_t)n_query * cap * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n_query; i++) std::sort(indices + (size_t)i * cap, indices + (size_t)i * cap + std::min(counts[i], cap));
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_get_sm_transform(sphsm_handle *h, float cm[3], float ocm[3], float xform[27]) {
+    if (!h || !cm || !ocm || !xform) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    SmState s;
+    CU(cudaMemcpyAsync(&s, h->sm, sizeof s, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(cm, s.cm, sizeof s.cm);
+    memcpy(ocm, s.ocm, sizeof s.ocm);
+    memcpy(xform, s.xform, sizeof s.xform);
+    return SPHSM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU entry points live in sphsm_comm.cuh once the slab layer is built; until then they report so.
+extern "C" int sphsm_comm_unique_id(void *) { return fail(nullptr, SPHSM_ERR_COMM, "multi-GPU layer not built yet"); }
+extern "C" int sphsm_comm_init(sphsm_handle *h, int, int, const void *) { return fail(h, SPHSM_ERR_COMM, "multi-GPU layer not built yet"); }
+extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int, int) { return fail(h, SPHSM_ERR_COMM, "multi-GPU layer not built yet"); }

@@ -1,0 +1,262 @@
+// sphsm_sort.cuh — subsystem (1): uniform-grid neighbour search.
+//   k_hash            cell key per particle (+ all radix-digit histograms in the same read)
+//   k_radix_pass      CUB-free LSD radix sort pass, 8-bit digits: one kernel per pass, per-tile stable ranking
+//                     with warp match/ballot, inter-tile digit prefixes by decoupled look-back, tile staged in
+//                     shared memory so the scatter leaves the SM as coalesced runs
+//   k_cell_order_fix  (strict mode) in-cell order = ascending ORIGINAL index, the reference's bucket order
+//   k_cell_bounds     cell_start table (num_cells + 2 entries, prefix form: cell c = [start[c], start[c+1]))
+//   k_reorder         gather the SoA state into the new slot order
+// Replaces Find_neighbors / Calculate_Cell_Position / Calculate_Cell_Hash, reference cpp:127-146, 199-213.
+#pragma once
+#include "sphsm_types.cuh"
+
+namespace sphsm {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_IPT = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_IPT;  // 4096 keys per tile
+constexpr int MAX_SORT_PASSES = 4;
+
+constexpr uint32_t TS_FLAG_AGG = 1u << 30;   // tile aggregate published
+constexpr uint32_t TS_FLAG_INCL = 2u << 30;  // inclusive prefix published
+constexpr uint32_t TS_MASK = (1u << 30) - 1;
+
+// ---- cell key + digit histograms ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hash(const __grid_constant__ DevParams p, const float4 *__restrict__ P,
+                                              uint32_t *__restrict__ keys, uint32_t *__restrict__ ghist /*passes*256*/,
+                                              int passes) {
+    __shared__ uint32_t s_hist[MAX_SORT_PASSES * RADIX];
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x; base < p.n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool valid = i < p.n;
+        const uint32_t active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            float4 q = P[i];
+            int ca, cb, cc;
+            uint32_t key = cell_coords(p, q.x, q.y, q.z, ca, cb, cc) ? (uint32_t)cell_key(p, ca, cb, cc) : (uint32_t)p.num_cells;
+            keys[i] = key;
+            // neighbouring slots share cells, hence digits: aggregate per warp before touching shared memory
+            for (int k = 0; k < passes; k++) {
+                uint32_t d = (key >> (k * RADIX_BITS)) & (RADIX - 1);
+                uint32_t peers = __match_any_sync(active, d);
+                if (lane == __ffs(peers) - 1) atomicAdd(&s_hist[k * RADIX + d], (uint32_t)__popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * RADIX; i += blockDim.x) {
+        uint32_t v = s_hist[i];
+        if (v) atomicAdd(&ghist[i], v);
+    }
+}
+
+__device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// exclusive scan of one value per thread over a 256-thread block
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t *s_warp /*8*/, uint32_t &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) {
+        uint32_t t = s_warp[w];
+        if (w < warp) wbase += t;
+        tot += t;
+    }
+    total = tot;
+    __syncthreads();
+    return wbase + inc - v;
+}
+
+// One LSD pass.  vin == nullptr means "values are the identity" (first pass).
+__global__ void __launch_bounds__(SORT_THREADS)
+k_radix_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
+             uint32_t *__restrict__ vout, int n, int shift, const uint32_t *__restrict__ ghist /*256, this pass*/,
+             uint32_t *tile_state /*tiles*256, zeroed*/, uint32_t *tile_counter /*zeroed*/) {
+    __shared__ uint32_t s_warp_hist[SORT_WARPS][RADIX];
+    __shared__ uint32_t s_local_start[RADIX];
+    __shared__ uint32_t s_out_base[RADIX];
+    __shared__ uint32_t s_keys[SORT_TILE];
+    __shared__ uint32_t s_vals[SORT_TILE];
+    __shared__ uint32_t s_scan[SORT_WARPS];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);  // ticket: lower tiles are always already running
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) s_warp_hist[w][tid] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int base = (int)tile * SORT_TILE;
+    const int tile_count = min(SORT_TILE, n - base);
+
+    // warp-striped load: element e = warp*512 + r*32 + lane keeps tile order == (warp, round, lane) order
+    uint32_t key[SORT_IPT], val[SORT_IPT];
+    uint16_t rank[SORT_IPT];
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; r++) {
+        int e = warp * (32 * SORT_IPT) + r * 32 + lane;
+        int idx = base + e;
+        bool ok = e < tile_count;
+        key[r] = ok ? kin[idx] : 0xffffffffu;  // pads rank last (stable) and are never written out
+        val[r] = ok ? (vin ? vin[idx] : (uint32_t)idx) : 0u;
+    }
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; r++) {
+        uint32_t d = (key[r] >> shift) & (RADIX - 1);
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t prev = 0;
+        if (lane == leader) {
+            prev = s_warp_hist[warp][d];
+            s_warp_hist[warp][d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[r] = (uint16_t)(prev + __popc(peers & lanemask_lt));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d owns digit d: warp-exclusive bases and the tile total
+    uint32_t tot = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; w++) {
+        uint32_t t = s_warp_hist[w][tid];
+        s_warp_hist[w][tid] = tot;
+        tot += t;
+    }
+    // decoupled look-back over earlier tiles for the global prefix of digit d
+    uint32_t excl = 0;
+    uint32_t *my = tile_state + (size_t)tile * RADIX + tid;
+    if (tile == 0) {
+        st_volatile(my, TS_FLAG_INCL | tot);
+    } else {
+        st_volatile(my, TS_FLAG_AGG | tot);
+        int t = (int)tile - 1;
+        while (true) {
+            uint32_t s = ld_volatile(tile_state + (size_t)t * RADIX + tid);
+            uint32_t flag = s & ~TS_MASK;
+            if (flag == 0) continue;  // not published yet: spin
+            excl += s & TS_MASK;
+            if (flag == TS_FLAG_INCL) break;
+            t--;
+        }
+        st_volatile(my, TS_FLAG_INCL | ((excl + tot) & TS_MASK));
+    }
+    // global start of digit d (exclusive scan of the global histogram) and local start inside the tile
+    uint32_t dummy;
+    uint32_t gstart = block_excl_scan_256(ghist[tid], s_scan, dummy);
+    uint32_t lstart = block_excl_scan_256(tot, s_scan, dummy);
+    s_local_start[tid] = lstart;
+    s_out_base[tid] = gstart + excl - lstart;  // out index = s_out_base[d] + (position inside the sorted tile)
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; r++) {
+        uint32_t d = (key[r] >> shift) & (RADIX - 1);
+        uint32_t pos = s_local_start[d] + s_warp_hist[warp][d] + rank[r];
+        s_keys[pos] = key[r];
+        s_vals[pos] = val[r];
+    }
+    __syncthreads();
+    for (int i = tid; i < tile_count; i += SORT_THREADS) {
+        uint32_t k = s_keys[i];
+        uint32_t d = (k >> shift) & (RADIX - 1);
+        uint32_t o = s_out_base[d] + (uint32_t)i;
+        kout[o] = k;
+        vout[o] = s_vals[i];
+    }
+}
+
+// strict mode: the reference's bucket order is ascending particle index (push_back order, cpp:207-212).
+// One thread per sorted slot that starts a cell: insertion-sort that cell's source slots by original index.
+__global__ void k_cell_order_fix(const uint32_t *__restrict__ keys, uint32_t *vals, const int *__restrict__ id_src, int n) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t k = keys[s];
+    if (s > 0 && keys[s - 1] == k) return;
+    int e = s + 1;
+    while (e < n && keys[e] == k) e++;
+    for (int i = s + 1; i < e; i++) {
+        uint32_t v = vals[i];
+        int vid = id_src[v];
+        int j = i - 1;
+        while (j >= s && id_src[vals[j]] > vid) {
+            vals[j + 1] = vals[j];
+            j--;
+        }
+        vals[j + 1] = v;
+    }
+}
+
+// cell_start[c] = first sorted slot with key >= c, for c in [0, num_cells + 1]; cell_start[num_cells + 1] = n.
+// Each boundary between different keys fills the gap of (possibly many) empty cells warp-cooperatively.
+__global__ void __launch_bounds__(256) k_cell_bounds(const uint32_t *__restrict__ keys, int *__restrict__ cell_start, int n, int num_cells) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    // slot s (0..n) closes the key gap (prev, cur]: prev = key[s-1] (or -1), cur = key[s] (or num_cells+1 at s == n)
+    int prev = 0, cur = -1;
+    if (s <= n) {
+        prev = (s == 0) ? -1 : (int)keys[s - 1];
+        cur = (s == n) ? num_cells + 1 : (int)keys[s];
+    }
+    int gap = cur - prev;  // number of cell_start entries this slot must write (0 for most slots)
+    if (gap < 0) gap = 0;
+    if (gap > 0 && gap <= 4) {
+        for (int c = prev + 1; c <= cur; c++) cell_start[c] = s;
+        gap = 0;
+    }
+    uint32_t pending = __ballot_sync(0xffffffffu, gap > 0);
+    while (pending) {
+        int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        int lo = __shfl_sync(0xffffffffu, prev, src) + 1;
+        int hi = __shfl_sync(0xffffffffu, cur, src);
+        int val = __shfl_sync(0xffffffffu, s, src);
+        for (int c = lo + lane; c <= hi; c += 32) cell_start[c] = val;
+    }
+}
+
+// gather into the new slot order; `all` also permutes the intermediate / diagnostic arrays (after an upload, or
+// in diagnostics mode, they are live across a re-sort)
+__global__ void __launch_bounds__(256) k_reorder(int n, const uint32_t *__restrict__ vals, Arrays src, Arrays dst, int all) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t v = vals[s];
+    dst.P[s] = src.P[v];
+    dst.VEL[s] = src.VEL[v];
+    dst.O[s] = src.O[v];
+    dst.E[s] = src.E[v];
+    dst.ID[s] = src.ID[v];
+    if (all) {
+        dst.C[s] = src.C[v];
+        dst.V[s] = src.V[v];
+        dst.S[s] = src.S[v];
+        dst.ACC[s] = src.ACC[v];
+        dst.GOAL[s] = src.GOAL[v];
+        dst.PV[s] = src.PV[v];
+    }
+}
+
+}  // namespace sphsm

@@ -1,0 +1,210 @@
+"""GPU: behaviour of the class-level API (init, stimulation / fixation control, accessors, error paths) against the
+oracle, plus size-independent properties of the neighbour search at sizes the oracle cannot reach."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import CpuSim
+from sph_sm_monodomain_b200 import inputs
+from tests.common import bits_equal, load_golden
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["pos", "vel", "predicted_vel", "inter_vel", "corrected_vel", "acc", "mass", "orig", "goal", "fixed", "dens", "pres",
+          "Vm", "Inter_Vm", "Iion", "stim", "w"]
+
+
+@pytest.fixture(scope="module")
+def Sim():
+    from sph_sm_monodomain_b200 import Sim as S
+
+    return S
+
+
+def both(Sim, pos, **kw):
+    a, b = CpuSim("port", **kw), Sim(**kw)
+    a.Init_Fluid(pos)
+    b.Init_Fluid(pos)
+    return a, b
+
+
+def same(a, b, fields=FIELDS):
+    pa, pb = a.particles(), b.particles()
+    return [f for f in fields if not bits_equal(pa[f], pb[f])]
+
+
+def test_init_fluid_matches_reference_and_drops_overflow(Sim):
+    pos = inputs.init_cube_positions()
+    a, b = both(Sim, pos, capacity=3000)
+    assert a.n == b.n == 3000  # cpp:103: particles beyond Max_Number_Paticles are silently dropped
+    assert same(a, b) == []
+    b.Init_Fluid(pos[:10])
+    assert b.n == 3000
+
+
+def test_init_fluid_appends(Sim):
+    pos = inputs.init_cube_positions()
+    a, b = both(Sim, pos[:1000])
+    a.Init_Fluid(pos[1000:1500])
+    b.Init_Fluid(pos[1000:1500])
+    assert a.n == b.n == 1500 and same(a, b) == []
+
+
+def test_stim_mesh_cube_setstim_off(Sim):
+    g, _ = load_golden("cfg1_4944")
+    pos = g["positions"]
+    a, b = both(Sim, pos)
+    a.turnOnStim_Mesh(pos)
+    b.turnOnStim_Mesh(pos)
+    assert same(a, b) == [] and a.particles()["fixed"].sum() == 1675
+    a.turnOffStim()
+    b.turnOffStim()
+    assert same(a, b) == []
+    cube = inputs.init_cube_positions()
+    a, b = both(Sim, cube)
+    a.turnOnStim_Cube(cube)
+    b.turnOnStim_Cube(cube)
+    assert same(a, b) == []
+    p = b.particles()
+    assert p["fixed"].sum() == 34 and (p["stim"] > 0).sum() == 578
+    # set_stim compares the SQUARED distance with `radius` (Q11)
+    a, b = both(Sim, cube)
+    for s in (a, b):
+        s.set_stim((0.6, 0.1, 0.6), 0.004, 123.0)
+    assert same(a, b) == [] and 0 < (b.particles()["stim"] == 123.0).sum() < len(cube)
+
+
+def test_aos_round_trip_and_positions(Sim):
+    rng = np.random.Generator(np.random.PCG64(5))
+    g, _ = load_golden("cube_4913")
+    a, b = both(Sim, g["positions"])
+    p = a.particles().copy()
+    for f in FIELDS:
+        if f == "fixed":
+            p[f] = rng.integers(0, 2, len(p))
+        else:
+            p[f] = rng.random(p[f].shape, dtype=np.float32) + np.float32(0.25)
+    b.upload(p)
+    q = b.particles()
+    for f in FIELDS:
+        assert bits_equal(p[f], q[f]), f
+    assert bits_equal(b.positions(), p["pos"])
+    # order survives a re-sort: Find_neighbors permutes the device arrays, the caller's order must not change
+    b.stage("Find_neighbors")
+    q = b.particles()
+    for f in FIELDS:
+        assert bits_equal(p[f], q[f]), f
+
+
+def test_fixed_particles_keep_goal_and_predicted_velocity(Sim):
+    """mFixed particles never get predicted_vel / mGoalPos rewritten (cpp:228,326): values uploaded for them persist."""
+    g, _ = load_golden("cube_4913")
+    a, b = both(Sim, g["positions"])
+    a.turnOnStim_Cube(g["positions"])
+    p = a.particles()
+    fixed = p["fixed"] != 0
+    p["predicted_vel"][fixed] = np.float32([0.25, -0.5, 0.125])
+    p["goal"][fixed] += np.float32(0.01)
+    b.upload(p)
+    a.Animation(3)
+    b.Animation(3)
+    pa, pb = a.particles(), b.particles()
+    assert bits_equal(pa["predicted_vel"][fixed], pb["predicted_vel"][fixed])
+    assert bits_equal(pa["goal"][fixed], pb["goal"][fixed])
+    assert np.abs(pa["pos"] - pb["pos"]).max() < 1e-6
+
+
+def test_parameter_toggles(Sim):
+    b = Sim()
+    assert b.flip_quadratic() is True and b.flip_quadratic() is False
+    assert b.flip_volume() is False and b.flip_volume() is True
+    a = CpuSim("port")
+    for v in (-30.0, -500.0, 12.5):
+        a.add_viscosity(v)
+        b.add_viscosity(v)
+        assert np.float32(b.get_params().mu) == a.constants()["mu"]
+    assert b.Get_stand_dens() == 1112.0 and b.Get_World_Size() == (1.5, 1.5, 1.5)
+    assert b.num_cells == 54872
+
+
+def test_error_paths(Sim):
+    from sph_sm_monodomain_b200 import SphsmError, _capi
+
+    lib = _capi.load()
+    p = _capi.Params()
+    lib.sphsm_default_params(p)
+    h = C.c_void_p()
+    p.struct_size = 4
+    assert lib.sphsm_create(p, C.byref(h)) == -1 and b"struct_size" in lib.sphsm_last_error(None)
+    lib.sphsm_default_params(p)
+    p.device = 99
+    assert lib.sphsm_create(p, C.byref(h)) == -2
+    b = Sim(capacity=100)
+    with pytest.raises(SphsmError):
+        b.upload(np.zeros(101, dtype=b.particles().dtype))
+    with pytest.raises(SphsmError):
+        b.stage(42)
+    with pytest.raises(SphsmError):
+        b.set_params(kernel_h=0.05)
+    b.Animation(3)  # zero particles: a no-op, like the reference's empty loops
+    assert b.n == 0 and b.total_time_steps == 3
+
+
+def test_single_particle_and_out_of_grid(Sim):
+    """N == 1: projectPositions returns early (cpp:236) and the goal stays; isolated-particle density is 9791.76."""
+    a, b = both(Sim, np.asarray([[0.5, 0.5, 0.5]], np.float32))
+    for s in (a, b):
+        s.set_stim((0.5, 0.5, 0.5), 0.01, 300.0)
+        s.Animation(4)
+    pa, pb = a.particles(), b.particles()
+    assert pb["dens"][0] == pytest.approx(9791.76, rel=1e-6)
+    for f in ("pos", "vel", "goal", "dens", "pres", "Vm"):
+        assert np.allclose(pa[f], pb[f], rtol=1e-6, atol=1e-9), f
+
+
+def test_walls_reflect_and_clamp(Sim):
+    rng = np.random.Generator(np.random.PCG64(11))
+    n = 600
+    pos = (rng.random((n, 3), dtype=np.float32) * np.float32(1.5)).astype(np.float32)
+    vel = (rng.standard_normal((n, 3)) * 40).astype(np.float32)
+    a, b = both(Sim, pos)
+    for s in (a, b):
+        s.set_fields(vel=vel, stim=np.full(n, 300, np.float32))
+    c = Sim(strict=True)
+    c.upload(b.particles())
+    a.Animation(25)
+    c.Animation(25)
+    pa, pc = a.particles(), c.particles()
+    for f in ("pos", "vel", "Vm", "dens"):
+        assert bits_equal(pa[f], pc[f]), f
+    assert pc["pos"].min() >= 0.0 and pc["pos"].max() <= 1.5
+
+
+# ---- properties at sizes the oracle cannot reach ----------------------------------------------------------------
+@pytest.mark.parametrize("n,world", [(1_000_000, (3.68, 3.68, 3.68)), (300_000, (18.52, 4.6, 4.6))])
+def test_large_random_cloud_grid_properties(Sim, n, world):
+    """Radix sort + cell table at 1M particles / up to 6M cells: the CSR is a permutation, every particle sits in the
+    bucket numpy computes for it, buckets are ascending, and sampled candidate sets equal brute force."""
+    rng = np.random.Generator(np.random.PCG64(17))
+    w = np.asarray(world, np.float32)
+    pos = (rng.random((n, 3), dtype=np.float32) * (w - np.float32(0.001))).astype(np.float32)
+    sim = Sim(capacity=n, world=world, diagnostics=False)
+    sim.Init_Fluid(pos)
+    sim.stage("Find_neighbors")
+    start, idx = sim.cells_csr()
+    assert start[-1] == n and np.array_equal(np.sort(idx), np.arange(n))
+    h = np.float32(0.04)
+    cell = (pos / h).astype(np.int32)
+    G = np.ceil(w / h).astype(np.int64)
+    hsh = cell[:, 0] + G[0] * (cell[:, 1] + G[1] * cell[:, 2])
+    owner = np.repeat(np.arange(len(start) - 1), np.diff(start))
+    assert np.array_equal(hsh[idx], owner)
+    same_cell = owner[1:] == owner[:-1]
+    assert np.all(idx[1:][same_cell] > idx[:-1][same_cell])
+    query = rng.integers(0, n, 64).astype(np.int32)
+    got = sim.neighbor_sets(query, 0, cap=2048)
+    for q, gq in zip(query, got):
+        near = np.all(np.abs(cell - cell[q]) <= 1, axis=1)
+        assert np.array_equal(gq, np.flatnonzero(near)), int(q)
+    assert bits_equal(sim.positions(), pos)

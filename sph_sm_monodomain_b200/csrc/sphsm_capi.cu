@@ -757,6 +757,7 @@ template <bool STRICT>
 static int run_stage(sphsm_handle *h, int stage) {
     const int n = h->n;
     int rc;
+    if (stage < SPHSM_STAGE_FIND_NEIGHBORS || stage > SPHSM_STAGE_UPDATE) return fail(h, SPHSM_ERR_INVALID, "unknown stage id");
     if (n == 0) return SPHSM_OK;
     if ((stage == 3 || stage == 4 || stage == 6) && !h->grid_valid && (rc = build_grid(h, nullptr)) != 0) return rc;
     switch (stage) {

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,6 +14,7 @@
 #include <vector>
 
 #include "sphsm_pass.cuh"
+#include "sphsm_pass2.cuh"
 #include "sphsm_sm.cuh"
 #include "sphsm_sort.cuh"
 #include "sphsm_types.cuh"
@@ -36,6 +38,8 @@ static const char *kGroupNames[SPHSM_NUM_KERNEL_GROUPS] = {"hash", "radix_sort",
 struct sphsm_handle {
     sphsm_params prm;
     DevParams dp;
+    DevParams *d_dp = nullptr;  // global-memory copy of dp for the fast passes (sphsm_pass2.cuh)
+    DevParams dp_uploaded{};
     int n = 0;
     cudaStream_t stream = nullptr;
     Arrays cur{}, alt{};
@@ -78,10 +82,20 @@ struct sphsm_handle {
         }                                                                                          \
     } while (0)
 
-#define LAUNCH(kern, grid, block, ...)                       \
-    do {                                                     \
-        kern<<<(grid), (block), 0, h->stream>>>(__VA_ARGS__); \
-        h->launches++;                                       \
+// SPHSM_SYNC_DEBUG=1 in the environment synchronises after every launch and names the kernel that faulted
+static const bool g_sync_debug = getenv("SPHSM_SYNC_DEBUG") != nullptr;
+#define LAUNCH(kern, grid, block, ...)                                                                  \
+    do {                                                                                                \
+        kern<<<(grid), (block), 0, h->stream>>>(__VA_ARGS__);                                           \
+        h->launches++;                                                                                  \
+        if (g_sync_debug) {                                                                             \
+            cudaError_t e_ = cudaStreamSynchronize(h->stream);                                          \
+            if (e_ != cudaSuccess) {                                                                    \
+                h->err = std::string("kernel ") + #kern + " failed: " + cudaGetErrorString(e_);         \
+                fprintf(stderr, "[sphsm] %s\n", h->err.c_str());                                        \
+                return SPHSM_ERR_CUDA;                                                                  \
+            }                                                                                           \
+        }                                                                                               \
     } while (0)
 
 static int fail(sphsm_handle *h, int code, const char *msg) {
@@ -194,7 +208,8 @@ static int alloc_arrays(sphsm_handle *h, Arrays &a, int cap, bool with_cold) {
     CU(cudaMalloc(&a.P, n4)); CU(cudaMalloc(&a.VEL, n4)); CU(cudaMalloc(&a.O, n4)); CU(cudaMalloc(&a.E, n4));
     CU(cudaMalloc(&a.ID, (size_t)cap * sizeof(int)));
     CU(cudaMalloc(&a.C, n4)); CU(cudaMalloc(&a.V, n4)); CU(cudaMalloc(&a.S, (size_t)cap * sizeof(float2)));
-    CU(cudaMalloc(&a.ACC, n4)); CU(cudaMalloc(&a.GOAL, n4)); CU(cudaMalloc(&a.PV, n4));
+    CU(cudaMalloc(&a.ACC, n4)); CU(cudaMalloc(&a.GOAL, n4)); CU(cudaMalloc(&a.PV, n4)); CU(cudaMalloc(&a.PB, n4));
+    CU(cudaMemset(a.PB, 0, n4));
     CU(cudaMemset(a.C, 0, n4)); CU(cudaMemset(a.V, 0, n4)); CU(cudaMemset(a.S, 0, (size_t)cap * sizeof(float2)));
     CU(cudaMemset(a.ACC, 0, n4)); CU(cudaMemset(a.GOAL, 0, n4)); CU(cudaMemset(a.PV, 0, n4));
     if (with_cold) {
@@ -205,7 +220,7 @@ static int alloc_arrays(sphsm_handle *h, Arrays &a, int cap, bool with_cold) {
 }
 static void free_arrays(Arrays &a, bool with_cold) {
     cudaFree(a.P); cudaFree(a.VEL); cudaFree(a.O); cudaFree(a.E); cudaFree(a.ID); cudaFree(a.C); cudaFree(a.V);
-    cudaFree(a.S); cudaFree(a.ACC); cudaFree(a.GOAL); cudaFree(a.PV);
+    cudaFree(a.S); cudaFree(a.ACC); cudaFree(a.GOAL); cudaFree(a.PV); cudaFree(a.PB);
     if (with_cold) { cudaFree(a.COLD_GOAL); cudaFree(a.COLD_PV); }
 }
 
@@ -259,6 +274,7 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaMalloc(&h->tile_state, (size_t)MAX_SORT_PASSES * h->max_tiles * RADIX * sizeof(uint32_t)));
     CU(cudaMalloc(&h->tile_counter, MAX_SORT_PASSES * sizeof(uint32_t)));
     CU(cudaMalloc(&h->slot_of, (size_t)cap * sizeof(int)));
+    CU(cudaMalloc(&h->d_dp, sizeof(DevParams)));
     CU(cudaMalloc(&h->sm, sizeof(SmState)));
     CU(cudaMemset(h->sm, 0, sizeof(SmState)));
     cudaDeviceProp prop;
@@ -283,7 +299,7 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     free_arrays(h->alt, false);
     for (int k = 0; k < 2; k++) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
     cudaFree(h->ghist); cudaFree(h->tile_state); cudaFree(h->tile_counter); cudaFree(h->cell_start); cudaFree(h->slot_of);
-    cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
+    cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
     cudaFree(h->d_itmp);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ev_step0) cudaEventDestroy(h->ev_step0);
@@ -666,7 +682,7 @@ struct GroupTimer {  // records an event at each kernel-group boundary while pro
 
 static void swap_sets(sphsm_handle *h, bool all) {
     std::swap(h->cur.P, h->alt.P); std::swap(h->cur.VEL, h->alt.VEL); std::swap(h->cur.O, h->alt.O);
-    std::swap(h->cur.E, h->alt.E); std::swap(h->cur.ID, h->alt.ID);
+    std::swap(h->cur.E, h->alt.E); std::swap(h->cur.ID, h->alt.ID); std::swap(h->cur.PB, h->alt.PB);
     if (all) {
         std::swap(h->cur.C, h->alt.C); std::swap(h->cur.V, h->alt.V); std::swap(h->cur.S, h->alt.S);
         std::swap(h->cur.ACC, h->alt.ACC); std::swap(h->cur.GOAL, h->alt.GOAL); std::swap(h->cur.PV, h->alt.PV);
@@ -797,13 +813,24 @@ static int fused_step(sphsm_handle *h) {
     int rc;
     if (n == 0) return SPHSM_OK;
     const bool diag = h->prm.diagnostics != 0;
+    if (memcmp(&h->dp, &h->dp_uploaded, sizeof(DevParams)) != 0) {  // n or a tunable changed since the last upload
+        h->dp_uploaded = h->dp;
+        CU(cudaMemcpyAsync(h->d_dp, &h->dp_uploaded, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
+    }
     GroupTimer gt(h);
     if ((rc = build_grid(h, &gt)) != 0) return rc;
     if ((rc = corrected_velocity<STRICT>(h, diag, &gt)) != 0) return rc;
-    LAUNCH((k_pass_a<STRICT, true, true>), cdiv(n, 128), 128, h->dp, h->cur, h->cell_start);
-    gt.end_group(KG_PASS_A);
-    if (diag) LAUNCH((k_pass_b<STRICT, PB_FUSED_DIAG>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
-    else LAUNCH((k_pass_b<STRICT, PB_FUSED>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
+    if (STRICT) {
+        LAUNCH((k_pass_a<STRICT, true, true>), cdiv(n, 128), 128, h->dp, h->cur, h->cell_start);
+        gt.end_group(KG_PASS_A);
+        if (diag) LAUNCH((k_pass_b<STRICT, PB_FUSED_DIAG>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH((k_pass_b<STRICT, PB_FUSED>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
+    } else {
+        LAUNCH(k_pass_a2, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+        gt.end_group(KG_PASS_A);
+        if (diag) LAUNCH(k_pass_b2<true>, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b2<false>, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+    }
     std::swap(h->cur.P, h->alt.P);
     gt.end_group(KG_PASS_B);
     CU(cudaGetLastError());

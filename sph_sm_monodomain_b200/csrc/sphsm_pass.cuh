@@ -242,8 +242,11 @@ __global__ void __launch_bounds__(256) k_refresh_derived(int n, Arrays a, int vo
     const float m = a.P[i].w, dens = a.VEL[i].w;
     if (vol_old) a.C[i].w = __fdiv_rn(m, dens);
     if (vol_new_vm) {
+        const float4 p4 = a.P[i];
+        const float vm = a.E[i].x;
         a.V[i].w = __fdiv_rn(m, dens);
-        a.S[i].y = a.E[i].x;
+        a.S[i].y = vm;
+        a.PB[i] = make_float4(p4.x, p4.y, p4.z, vm);
     }
 }
 

@@ -244,11 +244,13 @@ __global__ void __launch_bounds__(256) k_reorder(int n, const uint32_t *__restri
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t v = vals[s];
-    dst.P[s] = src.P[v];
+    const float4 p4 = src.P[v], e4 = src.E[v];
+    dst.P[s] = p4;
     dst.VEL[s] = src.VEL[v];
     dst.O[s] = src.O[v];
-    dst.E[s] = src.E[v];
+    dst.E[s] = e4;
     dst.ID[s] = src.ID[v];
+    dst.PB[s] = make_float4(p4.x, p4.y, p4.z, e4.x);
     if (all) {
         dst.C[s] = src.C[v];
         dst.V[s] = src.V[v];

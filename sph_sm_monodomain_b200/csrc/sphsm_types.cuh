@@ -9,6 +9,7 @@
 //   C    float4  (corrected_vel.xyz, m/dens_old)   written by stage 2, gathered by pass A
 //   V    float4  (inter_vel.xyz,     m/dens_new)   written by pass A, gathered by pass B
 //   S    float2  (pres, Vm)                        written by pass A, gathered by pass B
+//   PB   float4  (pos.xyz, Vm)                     written by the reorder, gathered by pass B (fast path)
 //   ACC  float4  (acc.xyz, Inter_Vm)               staged / diagnostics mode only
 //   GOAL float4  (goal.xyz, -)  PV float4 (predicted_vel.xyz, -)   diagnostics mode only
 //   COLD_GOAL / COLD_PV float4 by ORIGINAL index: the frozen mGoalPos / predicted_vel of fixed particles
@@ -46,6 +47,7 @@ struct DevParams {
     // slab decomposition (multi-GPU): this rank's grid holds the planes [c_off, c_off + gcl) along perm[2]
     // (owned planes [slab_lo, slab_hi) plus one halo plane per interior side); single GPU: c_off = 0, gcl = gc.
     int c_off, gcl, slab_lo, slab_hi;
+    int zero;  // always 0; read from the global-memory copy of this block to build values ptxas cannot re-materialise
 };
 
 struct Arrays {
@@ -54,6 +56,7 @@ struct Arrays {
     float4 *C, *V;
     float2 *S;
     float4 *ACC, *GOAL, *PV;
+    float4 *PB;  // (pos.xyz, Vm): pass B's neighbour record, written by the reorder
     float4 *COLD_GOAL, *COLD_PV;
 };
 

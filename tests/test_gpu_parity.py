@@ -207,17 +207,19 @@ def test_fast_path_equals_diagnostics_path(Sim, name):
 
 @pytest.mark.parametrize("name", ["cfg1_4944", "cube_4913"])
 def test_staged_equals_fused(Sim, name):
-    """Calling the seven public stage methods one by one equals Animation() (fast path, same kernels' arithmetic)."""
+    """Calling the seven public stage methods one by one (the simple reference-order kernels) equals Animation() (the
+    fused two-phase kernels): one step from identical state within TOL; three steps with the amplified classes."""
     a, g = gpu_from_golden(Sim, name)
     b, _ = gpu_from_golden(Sim, name)
     params = make_params(g)
-    for _ in range(3):
+    fields = ("pos", "vel", "dens", "pres", "Vm", "Iion", "w", "acc", "Inter_Vm", "goal", "corrected_vel", "inter_vel", "predicted_vel")
+    for step in range(3):
         a.Animation(1)
         for st in range(1, 8):
             b.stage(st)
-    pa, pb = a.particles(), b.particles()
-    for f in ("pos", "vel", "dens", "pres", "Vm", "Iion", "w", "acc", "Inter_Vm", "goal", "corrected_vel", "inter_vel", "predicted_vel"):
-        assert_close(f, pb[f], pa[f], params, tol=1e-6)
+        pa, pb = a.particles(), b.particles()
+        for f in fields:
+            assert_close(f, pb[f], pa[f], params, tol=TOL if step == 0 else whole_step_tol(f, False))
 
 
 # --------------------------------------------------------------------------------------------------------

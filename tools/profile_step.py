@@ -27,3 +27,6 @@ sim.sync()
 sim.Animation(a.steps)
 sim.sync()
 print("ms/step", sim.last_step_ms() / a.steps, "launches", sim.launch_count())
+if os.environ.get("SPHSM_GROUPS"):
+    for k, v in sim.profile_step(5).items():
+        print(f"  {k:45s} {v * 1e3:9.1f} us")

@@ -689,10 +689,12 @@ static void swap_sets(sphsm_handle *h, bool all) {
     }
 }
 
-// Find_neighbors: hash -> radix sort -> cell table -> reorder
-static int build_grid(sphsm_handle *h, GroupTimer *gt) {
+// Find_neighbors: hash -> radix sort -> cell table -> reorder.  grid_sort() is the first half (keys + sorted
+// permutation), grid_finish() the second (cell table + gather into the new slot order).  The fast path runs the
+// shape-matching sums and solve BETWEEN the two halves (they do not depend on slot order) so that the gather can apply
+// stage 2's per-particle map while the values are in registers (k_reorder_goal).
+static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
     const int n = h->n;
-    if (n == 0) { h->grid_valid = true; return SPHSM_OK; }
     const int passes = h->sort_passes;
     const int tiles = cdiv(n, SORT_TILE);
     CU(cudaMemsetAsync(h->ghist, 0, MAX_SORT_PASSES * RADIX * sizeof(uint32_t), h->stream));
@@ -709,15 +711,37 @@ static int build_grid(sphsm_handle *h, GroupTimer *gt) {
     h->sorted_buf = src;
     if (h->prm.strict) LAUNCH(k_cell_order_fix, cdiv(n, 128), 128, h->keys[src], h->vals[src], h->cur.ID, n);
     if (gt) gt->end_group(KG_SORT);
+    return SPHSM_OK;
+}
+
+// fuse_goal: 0 = plain gather; 1 / 2 = gather + goal / predicted / corrected velocity (2 also stores GOAL and PV)
+static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal) {
+    const int n = h->n, src = h->sorted_buf;
     LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
-    const bool all = h->prm.diagnostics || h->inter_live;
-    LAUNCH(k_reorder, cdiv(n, 256), 256, n, h->vals[src], h->cur, h->alt, all ? 1 : 0);
-    swap_sets(h, all);
+    if (fuse_goal) {
+        if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm);
+        else LAUNCH(k_reorder_goal<false>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm);
+        swap_sets(h, false);
+        std::swap(h->cur.C, h->alt.C);
+        std::swap(h->cur.GOAL, h->alt.GOAL);
+        std::swap(h->cur.PV, h->alt.PV);
+    } else {
+        const bool all = h->prm.diagnostics || h->inter_live;
+        LAUNCH(k_reorder, cdiv(n, 256), 256, n, h->vals[src], h->cur, h->alt, all ? 1 : 0);
+        swap_sets(h, all);
+    }
     if (gt) gt->end_group(KG_GRID);
     CU(cudaGetLastError());
     h->grid_valid = true;
     h->slot_of_valid = false;
     return SPHSM_OK;
+}
+
+static int build_grid(sphsm_handle *h, GroupTimer *gt) {
+    if (h->n == 0) { h->grid_valid = true; return SPHSM_OK; }
+    int rc;
+    if ((rc = grid_sort(h, gt)) != 0) return rc;
+    return grid_finish(h, gt, 0);
 }
 
 static int ensure_slot_of(sphsm_handle *h) {
@@ -731,10 +755,10 @@ static int ensure_slot_of(sphsm_handle *h) {
 static int rest_moments(sphsm_handle *h) {
     const int n = h->n, B = h->red_blocks;
     LAUNCH(k_rest_pass1, B, 256, n, h->cur.P, h->cur.O, h->partial);
-    LAUNCH(k_sum_partials, 1, 256, h->partial, B, 5, h->totals);
+    LAUNCH(k_sum_partials_par, 5, 256, h->partial, B, 5, h->totals);
     LAUNCH(k_rest_finalize1, 1, 1, h->totals, h->sm);
     LAUNCH(k_rest_pass2, dim3(B, 10), 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
-    for (int r = 0; r < 10; r++) LAUNCH(k_sum_partials, 1, 256, h->partial + (size_t)r * B * 9, B, 9, h->totals + r * 9);
+    for (int r = 0; r < 10; r++) LAUNCH(k_sum_partials_par, 9, 256, h->partial + (size_t)r * B * 9, B, 9, h->totals + r * 9);
     LAUNCH(k_rest_finalize2, 1, 1, h->totals, h->sm, h->scratch);
     CU(cudaGetLastError());
     h->rest_dirty = false;
@@ -742,6 +766,20 @@ static int rest_moments(sphsm_handle *h) {
 }
 
 // calculate_corrected_velocity
+// the fast path's shape-matching transform of this step: moment sums (any slot order) + the single-thread solve
+static int sm_transform_fast(sphsm_handle *h) {
+    const int n = h->n;
+    int rc;
+    if (h->rest_dirty && (rc = rest_moments(h)) != 0) return rc;
+    const int B = h->red_blocks;
+    if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
+    else LAUNCH(k_moments<3>, B, 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
+    const int nacc = h->dp.quadratic ? 33 : 15;
+    LAUNCH(k_sum_partials_par, nacc, 256, h->partial, B, nacc, h->totals);
+    LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
+    return SPHSM_OK;
+}
+
 template <bool STRICT>
 static int corrected_velocity(sphsm_handle *h, bool diag, GroupTimer *gt) {
     const int n = h->n;
@@ -751,14 +789,7 @@ static int corrected_velocity(sphsm_handle *h, bool diag, GroupTimer *gt) {
         if (STRICT) {
             if ((rc = ensure_slot_of(h)) != 0) return rc;
             LAUNCH(k_sm_strict, 1, 1, h->dp, h->cur.P, h->cur.O, h->slot_of, h->sm, h->scratch);
-        } else {
-            if (h->rest_dirty && (rc = rest_moments(h)) != 0) return rc;
-            const int B = h->red_blocks;
-            if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
-            else LAUNCH(k_moments<3>, B, 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
-            LAUNCH(k_sum_partials, 1, 256, h->partial, B, h->dp.quadratic ? 33 : 15, h->totals);
-            LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
-        }
+        } else if ((rc = sm_transform_fast(h)) != 0) return rc;
     }
     if (gt) gt->end_group(KG_MOMENTS);
     const int keep_goal = n <= 1;  // projectPositions returned early: mGoalPos keeps its previous value
@@ -818,8 +849,16 @@ static int fused_step(sphsm_handle *h) {
         CU(cudaMemcpyAsync(h->d_dp, &h->dp_uploaded, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
     }
     GroupTimer gt(h);
-    if ((rc = build_grid(h, &gt)) != 0) return rc;
-    if ((rc = corrected_velocity<STRICT>(h, diag, &gt)) != 0) return rc;
+    if (!STRICT && n > 1) {
+        // sort -> shape-matching transform (slot-order independent) -> cell table + gather fused with stage 2's map
+        if ((rc = grid_sort(h, &gt)) != 0) return rc;
+        if ((rc = sm_transform_fast(h)) != 0) return rc;
+        gt.end_group(KG_MOMENTS);
+        if ((rc = grid_finish(h, &gt, diag ? 2 : 1)) != 0) return rc;
+    } else {
+        if ((rc = build_grid(h, &gt)) != 0) return rc;
+        if ((rc = corrected_velocity<STRICT>(h, diag, &gt)) != 0) return rc;
+    }
     if (STRICT) {
         LAUNCH((k_pass_a<STRICT, true, true>), cdiv(n, 128), 128, h->dp, h->cur, h->cell_start);
         gt.end_group(KG_PASS_A);

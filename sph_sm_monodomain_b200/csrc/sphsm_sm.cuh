@@ -387,21 +387,20 @@ __global__ void k_sm_strict(const __grid_constant__ DevParams p, const float4 *_
 }
 
 // goal position (cpp:324-329 / 429-444), predicted velocity (cpp:226-231), corrected velocity (cpp:661-666), and the
-// neighbour volume m/dens of the PREVIOUS step's density that pass A needs (Q10).
-template <bool STRICT, bool DIAG>
-__global__ void __launch_bounds__(256) k_goal_cvel(const __grid_constant__ DevParams p, Arrays a, const SmState *__restrict__ sm, int keep_goal) {
+// neighbour volume m/dens of the PREVIOUS step's density that pass A needs (Q10) — for one particle.
+// prev_goal: used instead of T*q + cm when projectPositions returned early (n <= 1, cpp:236).
+template <bool STRICT>
+__device__ __forceinline__ float4 goal_cvel_one(const DevParams &p, const SmState *__restrict__ sm, const float4 *__restrict__ cold_goal,
+                                                const float4 *__restrict__ cold_pv, const float4 q4, const float4 v4, const float4 o,
+                                                const float4 *prev_goal, float4 &goal, float4 &pv) {
     using A = Ar<STRICT>;
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n) return;
-    const float4 q4 = a.P[s], v4 = a.VEL[s], o = a.O[s];
     const int flags = __float_as_int(o.w);
     float gx, gy, gz, px, py, pz;
     if (!flags) {
         const float qx = A::sub(o.x, sm->ocm[0]), qy = A::sub(o.y, sm->ocm[1]), qz = A::sub(o.z, sm->ocm[2]);
         const float *T = sm->xform;
-        if (keep_goal) {
-            const float4 g4 = a.GOAL[s];
-            gx = g4.x; gy = g4.y; gz = g4.z;
+        if (prev_goal) {
+            gx = prev_goal->x; gy = prev_goal->y; gz = prev_goal->z;
         } else if (!p.quadratic) {
             gx = A::add(A::add(A::add(A::mul(T[0], qx), A::mul(T[1], qy)), A::mul(T[2], qz)), sm->cm[0]);
             gy = A::add(A::add(A::add(A::mul(T[3], qx), A::mul(T[4], qy)), A::mul(T[5], qz)), sm->cm[1]);
@@ -426,7 +425,7 @@ __global__ void __launch_bounds__(256) k_goal_cvel(const __grid_constant__ DevPa
         py = A::add(v4.y, A::div(A::mul(p.gravity[1], p.dt), q4.w));
         pz = A::add(v4.z, A::div(A::mul(p.gravity[2], p.dt), q4.w));
     } else {
-        const float4 cg = a.COLD_GOAL[flags - 1], cp = a.COLD_PV[flags - 1];
+        const float4 cg = cold_goal[flags - 1], cp = cold_pv[flags - 1];
         gx = cg.x; gy = cg.y; gz = cg.z;
         px = cp.x; py = cp.y; pz = cp.z;
     }
@@ -435,11 +434,61 @@ __global__ void __launch_bounds__(256) k_goal_cvel(const __grid_constant__ DevPa
     c.y = A::add(py, A::mul(A::mul(A::sub(gy, q4.y), p.inv_dt), p.alpha));
     c.z = A::add(pz, A::mul(A::mul(A::sub(gz, q4.z), p.inv_dt), p.alpha));
     c.w = __fdiv_rn(q4.w, v4.w);  // np->mass / np->dens with the previous step's density, cpp:696
-    a.C[s] = c;
+    goal = make_float4(gx, gy, gz, 0.0f);
+    pv = make_float4(px, py, pz, 0.0f);
+    return c;
+}
+
+template <bool STRICT, bool DIAG>
+__global__ void __launch_bounds__(256) k_goal_cvel(const __grid_constant__ DevParams p, Arrays a, const SmState *__restrict__ sm, int keep_goal) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    float4 goal, pv, prev;
+    if (keep_goal) prev = a.GOAL[s];
+    a.C[s] = goal_cvel_one<STRICT>(p, sm, a.COLD_GOAL, a.COLD_PV, a.P[s], a.VEL[s], a.O[s], keep_goal ? &prev : nullptr, goal, pv);
     if (DIAG) {
-        a.GOAL[s] = make_float4(gx, gy, gz, 0.0f);
-        a.PV[s] = make_float4(px, py, pz, 0.0f);
+        a.GOAL[s] = goal;
+        a.PV[s] = pv;
     }
+}
+
+// Fused fast path: gather the persistent state into the new slot order AND apply stage 2's per-particle map while the
+// values are in registers (the shape-matching transform of this step was already solved at the end of the previous
+// step from pass B's moment partials).  Saves the separate 48 B/particle re-read of k_goal_cvel.
+template <bool DIAG>
+__global__ void __launch_bounds__(256) k_reorder_goal(const __grid_constant__ DevParams p, const uint32_t *__restrict__ vals, Arrays src,
+                                                      Arrays dst, const SmState *__restrict__ sm) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    const uint32_t v = vals[s];
+    const float4 p4 = src.P[v], v4 = src.VEL[v], o4 = src.O[v], e4 = src.E[v];
+    dst.P[s] = p4;
+    dst.VEL[s] = v4;
+    dst.O[s] = o4;
+    dst.E[s] = e4;
+    dst.ID[s] = src.ID[v];
+    dst.PB[s] = make_float4(p4.x, p4.y, p4.z, e4.x);
+    float4 goal, pv;
+    dst.C[s] = goal_cvel_one<false>(p, sm, src.COLD_GOAL, src.COLD_PV, p4, v4, o4, nullptr, goal, pv);
+    if (DIAG) {
+        dst.GOAL[s] = goal;
+        dst.PV[s] = pv;
+    }
+}
+
+// totals[k] = sum over blocks of partial[b * nacc + k]; one block per accumulator, fixed order (deterministic)
+__global__ void __launch_bounds__(256) k_sum_partials_par(const double *__restrict__ partial, int blocks, int nacc, double *totals) {
+    __shared__ double s[256];
+    const int k = blockIdx.x;
+    double v = 0.0;
+    for (int b = threadIdx.x; b < blocks; b += 256) v += partial[(size_t)b * nacc + k];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[k] = s[0];
 }
 
 }  // namespace sphsm

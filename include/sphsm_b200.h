@@ -44,7 +44,10 @@ typedef enum {
     SPHSM_STAGE_DENSITY_PRESSURE = 4,       /* Compute_Density_SingPressure, cpp:448-513 */
     SPHSM_STAGE_CELL_MODEL = 5,             /* calculate_cell_model, cpp:575-593 */
     SPHSM_STAGE_FORCE = 6,                  /* Compute_Force, cpp:515-573 */
-    SPHSM_STAGE_UPDATE = 7                  /* Update_Properties, cpp:598-651 */
+    SPHSM_STAGE_UPDATE = 7,                 /* Update_Properties, cpp:598-651 */
+    /* the two public sub-steps of stage 2 (h:127-129); sphsm_step never issues them separately */
+    SPHSM_STAGE_EXTERNAL_FORCES = 8,        /* apply_external_forces, cpp:215-232: predicted_vel only */
+    SPHSM_STAGE_PROJECT_POSITIONS = 9       /* projectPositions, cpp:234-446: mGoalPos only */
 } sphsm_stage_id;
 
 /* Every tunable the reference hard-codes in its ctor (cpp:13-69) or in-class initialisers (h:72-94).

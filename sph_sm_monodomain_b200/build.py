@@ -30,6 +30,36 @@ def _sources():
     return srcs
 
 
+HOST = os.path.join(HERE, "host")
+DROPIN_INC = os.path.join(ROOT, "include", "dropin")
+DROPIN_LIB = os.path.join(HERE, "libsphsm_dropin.so")
+HEADLESS = os.path.join(HERE, "sphsm_headless")
+
+
+def build_dropin(force: bool = False) -> str:
+    """g++ -> libsphsm_dropin.so (the reference-compatible C++ class over the C-ABI) and the headless driver that
+    replays main.cpp's run protocol.  Host C++11 only, like the reference; links against libsphsm_b200.so."""
+    srcs = [os.path.join(HOST, "SPH_SM_monodomain.cpp"), os.path.join(HOST, "headless_main.cpp"),
+            os.path.join(ROOT, "include", "sphsm_b200.h")] + [os.path.join(DROPIN_INC, f) for f in os.listdir(DROPIN_INC)]
+    outs = [DROPIN_LIB, HEADLESS]
+    if not force and all(os.path.exists(o) for o in outs) and min(os.path.getmtime(o) for o in outs) >= max(
+            max(os.path.getmtime(x) for x in srcs), os.path.getmtime(LIB)):
+        return DROPIN_LIB
+    cxx = os.environ.get("CXX", "g++")
+    common = [cxx, "-std=c++11", "-O2", "-Wall", "-fPIC", "-I", DROPIN_INC]
+    rpath = "-Wl,-rpath,$ORIGIN"
+    cmds = [
+        common + ["-shared", "-o", DROPIN_LIB, os.path.join(HOST, "SPH_SM_monodomain.cpp"), "-L", HERE, "-lsphsm_b200", rpath],
+        common + ["-o", HEADLESS, os.path.join(HOST, "headless_main.cpp"), "-L", HERE, "-lsphsm_dropin", "-lsphsm_b200", rpath],
+    ]
+    for cmd in cmds:
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+            raise RuntimeError("g++ failed building the drop-in class")
+    return DROPIN_LIB
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -56,3 +86,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_dropin(force="--force" in sys.argv))

@@ -781,11 +781,11 @@ static int sm_transform_fast(sphsm_handle *h) {
 }
 
 template <bool STRICT>
-static int corrected_velocity(sphsm_handle *h, bool diag, GroupTimer *gt) {
+static int corrected_velocity(sphsm_handle *h, bool diag, GroupTimer *gt, int store = 7) {
     const int n = h->n;
     if (n == 0) return SPHSM_OK;
     int rc;
-    if (n > 1) {  // projectPositions returns early for <= 1 particle, cpp:236
+    if (n > 1 && (store & 3)) {  // projectPositions returns early for <= 1 particle, cpp:236
         if (STRICT) {
             if ((rc = ensure_slot_of(h)) != 0) return rc;
             LAUNCH(k_sm_strict, 1, 1, h->dp, h->cur.P, h->cur.O, h->slot_of, h->sm, h->scratch);
@@ -793,8 +793,8 @@ static int corrected_velocity(sphsm_handle *h, bool diag, GroupTimer *gt) {
     }
     if (gt) gt->end_group(KG_MOMENTS);
     const int keep_goal = n <= 1;  // projectPositions returned early: mGoalPos keeps its previous value
-    if (diag || keep_goal) LAUNCH((k_goal_cvel<STRICT, true>), cdiv(n, 256), 256, h->dp, h->cur, h->sm, keep_goal);
-    else LAUNCH((k_goal_cvel<STRICT, false>), cdiv(n, 256), 256, h->dp, h->cur, h->sm, 0);
+    if (diag || keep_goal) LAUNCH((k_goal_cvel<STRICT, true>), cdiv(n, 256), 256, h->dp, h->cur, h->sm, keep_goal, store);
+    else LAUNCH((k_goal_cvel<STRICT, false>), cdiv(n, 256), 256, h->dp, h->cur, h->sm, 0, store);
     if (gt) gt->end_group(KG_GOAL);
     CU(cudaGetLastError());
     return SPHSM_OK;
@@ -804,7 +804,7 @@ template <bool STRICT>
 static int run_stage(sphsm_handle *h, int stage) {
     const int n = h->n;
     int rc;
-    if (stage < SPHSM_STAGE_FIND_NEIGHBORS || stage > SPHSM_STAGE_UPDATE) return fail(h, SPHSM_ERR_INVALID, "unknown stage id");
+    if (stage < SPHSM_STAGE_FIND_NEIGHBORS || stage > SPHSM_STAGE_PROJECT_POSITIONS) return fail(h, SPHSM_ERR_INVALID, "unknown stage id");
     if (n == 0) return SPHSM_OK;
     if ((stage == 3 || stage == 4 || stage == 6) && !h->grid_valid && (rc = build_grid(h, nullptr)) != 0) return rc;
     switch (stage) {
@@ -812,6 +812,10 @@ static int run_stage(sphsm_handle *h, int stage) {
             return build_grid(h, nullptr);
         case SPHSM_STAGE_CORRECTED_VELOCITY:
             return corrected_velocity<STRICT>(h, true, nullptr);
+        case SPHSM_STAGE_EXTERNAL_FORCES:  // predicted_vel only
+            return corrected_velocity<STRICT>(h, true, nullptr, 4);
+        case SPHSM_STAGE_PROJECT_POSITIONS:  // mGoalPos only
+            return corrected_velocity<STRICT>(h, true, nullptr, 2);
         case SPHSM_STAGE_INTERMEDIATE_VELOCITY:
             LAUNCH(k_refresh_derived, cdiv(n, 256), 256, n, h->cur, 1, 0);
             LAUNCH((k_pass_a<STRICT, false, true>), cdiv(n, 128), 128, h->dp, h->cur, h->cell_start);

@@ -439,16 +439,20 @@ __device__ __forceinline__ float4 goal_cvel_one(const DevParams &p, const SmStat
     return c;
 }
 
+// store: bit 0 = corrected_vel (C), bit 1 = mGoalPos, bit 2 = predicted_vel — the sub-stages apply_external_forces
+// (cpp:215-232) and projectPositions (cpp:234-446) store only their own output; the full stage stores all three.
 template <bool STRICT, bool DIAG>
-__global__ void __launch_bounds__(256) k_goal_cvel(const __grid_constant__ DevParams p, Arrays a, const SmState *__restrict__ sm, int keep_goal) {
+__global__ void __launch_bounds__(256) k_goal_cvel(const __grid_constant__ DevParams p, Arrays a, const SmState *__restrict__ sm, int keep_goal,
+                                                   int store) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
     float4 goal, pv, prev;
     if (keep_goal) prev = a.GOAL[s];
-    a.C[s] = goal_cvel_one<STRICT>(p, sm, a.COLD_GOAL, a.COLD_PV, a.P[s], a.VEL[s], a.O[s], keep_goal ? &prev : nullptr, goal, pv);
+    const float4 c = goal_cvel_one<STRICT>(p, sm, a.COLD_GOAL, a.COLD_PV, a.P[s], a.VEL[s], a.O[s], keep_goal ? &prev : nullptr, goal, pv);
+    if (store & 1) a.C[s] = c;
     if (DIAG) {
-        a.GOAL[s] = goal;
-        a.PV[s] = pv;
+        if (store & 2) a.GOAL[s] = goal;
+        if (store & 4) a.PV[s] = pv;
     }
 }
 

@@ -178,13 +178,28 @@ int sphsm_last_step_ms(sphsm_handle *h, float *ms);
 int sphsm_profile_step(sphsm_handle *h, int nsteps, float out_ms[SPHSM_NUM_KERNEL_GROUPS]);
 const char *sphsm_kernel_group_name(int group);
 
-/* ---- multi-GPU (one process per GPU; slab decomposition along params.slab_axis) ------------------------- */
-/* NCCL bootstrap: rank 0 calls sphsm_comm_unique_id (128 bytes) and shares it by any means (bench.py uses
- * torch.distributed); every rank then calls sphsm_comm_init on its own handle. */
+/* ---- multi-GPU (one process per GPU; slab decomposition along params.slab_axis; no reference counterpart) ------ */
+/* Protocol: every rank creates its handle with the same GLOBAL capacity / world and slab_axis = the longest axis, uploads
+ * the same global particle set (init_fluid / upload_aos / set_masks ...), then:
+ *   rank 0: sphsm_comm_unique_id(id) -> share the 128 bytes by any means (bench.py: torch.distributed broadcast)
+ *   all:    sphsm_comm_init(h, nranks, rank, id); sphsm_comm_set_slab(h, lo, hi)   (rank r owns cell planes [lo, hi))
+ * From then on sphsm_step includes the halo / migrant exchange (ncclSend / ncclRecv with the two slab neighbours) and
+ * the shape-matching moment allreduce, particle ids stay global, and download_aos / download_positions write only the
+ * particles this rank owns (n = global count).  params.reserved[0] overrides the per-message halo capacity.
+ * NCCL is resolved at run time (dlopen "libnccl.so.2", or $SPHSM_NCCL_LIB). */
 int sphsm_comm_unique_id(void *id128);
 int sphsm_comm_init(sphsm_handle *h, int nranks, int rank, const void *id128);
-/* Slab of this rank in cell planes [lo, hi) along slab_axis; particles outside are dropped at upload. */
 int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi);
+/* out: [0] comm mode (0 none, 1 NCCL, 2 local group) [1] nranks [2] rank [3] local slots (owned + halo)
+ *      [4] first owned slot [5] end of owned slots [6] halo message capacity [7] slab mode on */
+int sphsm_comm_info(sphsm_handle *h, int out8[8]);
+/* Compact read-back of the owned particles: original ids and positions (3 floats each); *count = owned particles. */
+int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int cap, int *count);
+/* Virtual ranks for testing the slab logic on ONE device: nranks handles (same device, capacity, world, slab_axis) form
+ * a local group whose collectives are device copies; after sphsm_comm_set_slab on each, sphsm_step_group advances all of
+ * them in lockstep through the same phases the NCCL path runs. */
+int sphsm_comm_init_local(sphsm_handle **handles, int nranks);
+int sphsm_step_group(sphsm_handle **handles, int nranks, int nsteps);
 
 const char *sphsm_last_error(sphsm_handle *h);
 

@@ -4,6 +4,7 @@
 #include "../../include/sphsm_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -13,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "sphsm_comm.cuh"
 #include "sphsm_pass.cuh"
 #include "sphsm_pass2.cuh"
 #include "sphsm_sm.cuh"
@@ -29,6 +31,7 @@ enum : int {
 };
 
 static std::string g_create_error;
+static int (*g_nccl_destroy)(void *) = nullptr;  // set once libnccl is loaded (sphsm_destroy runs before its definition)
 
 enum KernelGroup { KG_HASH = 0, KG_SORT, KG_GRID, KG_MOMENTS, KG_GOAL, KG_PASS_A, KG_PASS_B, KG_OTHER };
 static const char *kGroupNames[SPHSM_NUM_KERNEL_GROUPS] = {"hash", "radix_sort", "cell_bounds+reorder", "sm_moments+solve",
@@ -69,6 +72,18 @@ struct sphsm_handle {
     float group_ms[SPHSM_NUM_KERNEL_GROUPS] = {};
     int group_launches[SPHSM_NUM_KERNEL_GROUPS] = {};
     std::string err;
+    // ---- multi-GPU slab layer (sphsm_comm.cuh) ----
+    int comm_mode = 0;        // 0 none, 1 NCCL (one process per GPU), 2 local group (virtual ranks on one device, for tests)
+    int nranks = 1, rank = 0;
+    void *nccl_comm = nullptr;
+    bool slab_applied = false;
+    int send_cap = 0;         // particles per exchange-1 message
+    int alloc_n = 0;          // slots allocated per array (capacity + room for two halo messages in slab mode)
+    uint8_t *msg_send[2] = {nullptr, nullptr}, *msg_recv[2] = {nullptr, nullptr};  // [0] left neighbour, [1] right neighbour
+    int *d_err = nullptr, *d_meta = nullptr, *h_meta = nullptr;
+    int b2 = 0, b3 = 0;       // start of the 2nd / of the last owned plane (exchange-2 ranges)
+    int mom_n = 0;            // slab step: extent of the PRE-reorder arrays (old slots + both message regions) the moment sums scan
+    struct GroupTimer *gt = nullptr;
 };
 
 #define CU(call)                                                                                   \
@@ -103,6 +118,12 @@ static int fail(sphsm_handle *h, int code, const char *msg) {
     return code;
 }
 static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+static inline void set_n(sphsm_handle *h, int n) {  // single-GPU meaning: every slot is computed
+    h->n = n;
+    h->dp.n = n;
+    h->dp.own_begin = 0;
+    h->dp.own_end = n;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // defaults: the reference ctor, cpp:13-69, with its float/double promotions
@@ -178,6 +199,7 @@ static void derive_dev_params(sphsm_handle *h) {
     }
     d.ga = d.g[d.perm[0]]; d.gb = d.g[d.perm[1]]; d.gc = d.g[d.perm[2]];
     d.c_off = 0; d.gcl = d.gc; d.slab_lo = 0; d.slab_hi = d.gc;
+    d.slab_on = 0; d.own_begin = 0; d.own_end = h->n;
     d.num_cells = d.ga * d.gb * d.gcl;
     d.K = q.K; d.rho0 = q.stand_density; d.dt = q.time_delta; d.inv_dt = 1.0f / q.time_delta;  // cpp:661
     d.wall_hit = q.wall_hit; d.mu = q.mu; d.mix = q.velocity_mixing;
@@ -258,7 +280,14 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
         }
     }
     h = nh;
-    const int cap = p->capacity;
+    // slab mode appends up to two halo messages behind the local particles before every sort: room for them
+    if (p->slab_axis >= 0) {
+        int hc = p->reserved[0];  // halo capacity override (particles per message)
+        if (hc <= 0) hc = (int)(pow((double)p->capacity, 2.0 / 3.0)) + 4096;
+        h->send_cap = hc;
+    }
+    h->alloc_n = p->capacity + 2 * h->send_cap;
+    const int cap = h->alloc_n;
     int rc;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     if ((rc = alloc_arrays(h, h->cur, cap, true)) != 0) return rc;
@@ -301,6 +330,10 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     cudaFree(h->ghist); cudaFree(h->tile_state); cudaFree(h->tile_counter); cudaFree(h->cell_start); cudaFree(h->slot_of);
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
     cudaFree(h->d_itmp);
+    for (int k = 0; k < 2; k++) { cudaFree(h->msg_send[k]); cudaFree(h->msg_recv[k]); }
+    cudaFree(h->d_err); cudaFree(h->d_meta);
+    if (h->h_meta) cudaFreeHost(h->h_meta);
+    if (h->nccl_comm && g_nccl_destroy) g_nccl_destroy(h->nccl_comm);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ev_step0) cudaEventDestroy(h->ev_step0);
     if (h->ev_step1) cudaEventDestroy(h->ev_step1);
@@ -323,10 +356,11 @@ extern "C" int sphsm_set_params(sphsm_handle *h, const sphsm_params *p) {
     if (p->capacity != h->prm.capacity || p->device != h->prm.device || p->kernel_h != h->prm.kernel_h ||
         memcmp(p->world, h->prm.world, sizeof p->world) != 0 || p->slab_axis != h->prm.slab_axis)
         return fail(h, SPHSM_ERR_INVALID, "capacity, device, kernel_h, world and slab_axis are fixed at create");
-    const int c_off = h->dp.c_off, gcl = h->dp.gcl, lo = h->dp.slab_lo, hi = h->dp.slab_hi, nc = h->dp.num_cells;
+    const DevParams old = h->dp;
     h->prm = *p;
     derive_dev_params(h);
-    h->dp.c_off = c_off; h->dp.gcl = gcl; h->dp.slab_lo = lo; h->dp.slab_hi = hi; h->dp.num_cells = nc;
+    h->dp.c_off = old.c_off; h->dp.gcl = old.gcl; h->dp.slab_lo = old.slab_lo; h->dp.slab_hi = old.slab_hi; h->dp.num_cells = old.num_cells;
+    h->dp.slab_on = old.slab_on; h->dp.own_begin = old.own_begin; h->dp.own_end = old.own_end;
     return SPHSM_OK;
 }
 
@@ -357,9 +391,10 @@ __global__ void k_aos_to_soa(int first, int count, const uint8_t *__restrict__ a
     a.COLD_GOAL[i] = goal; a.COLD_PV[i] = pv;
 }
 
-__global__ void k_soa_to_aos(int n, Arrays a, uint8_t *__restrict__ aos, int stride) {
+__global__ void k_soa_to_aos(int first, int count, Arrays a, uint8_t *__restrict__ aos, int stride) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= count) return;
+    s += first;
     const int id = a.ID[s];
     uint8_t *r = aos + (size_t)id * stride;
     const float4 p = a.P[s], v = a.VEL[s], o = a.O[s], e = a.E[s], c = a.C[s], iv = a.V[s], acc = a.ACC[s];
@@ -381,9 +416,10 @@ __global__ void k_soa_to_aos(int n, Arrays a, uint8_t *__restrict__ aos, int str
     stf(r, OFF_IION, e.y); stf(r, OFF_STIM, e.w); stf(r, OFF_W, e.z);
 }
 
-__global__ void k_positions_out(int n, Arrays a, float *__restrict__ xyz) {
+__global__ void k_positions_out(int first, int count, Arrays a, float *__restrict__ xyz) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= count) return;
+    s += first;
     const int id = a.ID[s];
     const float4 p = a.P[s];
     xyz[3 * (size_t)id] = p.x; xyz[3 * (size_t)id + 1] = p.y; xyz[3 * (size_t)id + 2] = p.z;
@@ -515,7 +551,10 @@ static void state_changed(sphsm_handle *h, bool rest) {
     h->grid_valid = false;
     h->slot_of_valid = false;
     h->inter_live = true;
-    if (rest) h->rest_dirty = true;
+    if (rest) {
+        h->rest_dirty = true;
+        h->slab_applied = false;  // the particle set was replaced: sphsm_comm_set_slab must be applied again
+    }
 }
 
 extern "C" int sphsm_init_fluid(sphsm_handle *h, const float *xyz, int n) {
@@ -529,8 +568,7 @@ extern "C" int sphsm_init_fluid(sphsm_handle *h, const float *xyz, int n) {
     LAUNCH(k_init_particles, cdiv(take, 256), 256, h->n, take, h->d_tmp, h->cur, h->prm.particle_mass, h->prm.stand_density);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));  // xyz may be pageable / freed by the caller
-    h->n += take;
-    h->dp.n = h->n;
+    set_n(h, h->n + take);
     state_changed(h, true);
     return SPHSM_OK;
 }
@@ -545,21 +583,24 @@ extern "C" int sphsm_upload_aos(sphsm_handle *h, const void *particles, int n, i
     if (n > 0) LAUNCH(k_aos_to_soa, cdiv(n, 256), 256, 0, n, h->d_aos, stride, h->cur);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
-    h->n = n;
-    h->dp.n = n;
+    set_n(h, n);
     state_changed(h, true);
     return SPHSM_OK;
 }
 
 extern "C" int sphsm_download_aos(sphsm_handle *h, void *particles, int n, int stride) {
     if (!h || !particles || n < 0 || stride < SPHSM_PARTICLE_STRIDE) return SPHSM_ERR_INVALID;
-    if (n > h->n) return fail(h, SPHSM_ERR_INVALID, "n exceeds the number of particles");
+    // slab mode: n counts GLOBAL particles (the caller's array is indexed by original id); only the particles this rank
+    // owns are written, everything else in the caller's array keeps its bytes
+    const bool slab = h->dp.slab_on != 0;
+    if (n > (slab ? h->prm.capacity : h->n)) return fail(h, SPHSM_ERR_INVALID, "n exceeds the number of particles");
     CU(cudaSetDevice(h->prm.device));
     int rc;
-    if ((rc = ensure_aos(h, (size_t)std::max(h->n, 1) * stride)) != 0) return rc;
-    if (stride != SPHSM_PARTICLE_STRIDE)  // keep the caller's padding bytes: round-trip through the device image
+    if ((rc = ensure_aos(h, (size_t)std::max(std::max(h->n, n), 1) * stride)) != 0) return rc;
+    if (stride != SPHSM_PARTICLE_STRIDE || slab)  // keep the caller's other bytes: round-trip through the device image
         CU(cudaMemcpyAsync(h->d_aos, particles, (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
-    if (h->n > 0) LAUNCH(k_soa_to_aos, cdiv(h->n, 256), 256, h->n, h->cur, h->d_aos, stride);
+    const int nown = h->dp.own_end - h->dp.own_begin;
+    if (nown > 0) LAUNCH(k_soa_to_aos, cdiv(nown, 256), 256, h->dp.own_begin, nown, h->cur, h->d_aos, stride);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(particles, h->d_aos, (size_t)n * stride, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -567,11 +608,15 @@ extern "C" int sphsm_download_aos(sphsm_handle *h, void *particles, int n, int s
 }
 
 extern "C" int sphsm_download_positions(sphsm_handle *h, float *xyz, int n) {
-    if (!h || !xyz || n < 0 || n > h->n) return SPHSM_ERR_INVALID;
+    if (!h || !xyz || n < 0) return SPHSM_ERR_INVALID;
+    const bool slab = h->dp.slab_on != 0;  // slab mode: n is the GLOBAL count, only owned particles are written
+    if (n > (slab ? h->prm.capacity : h->n)) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
     int rc;
-    if ((rc = ensure_tmp(h, (size_t)std::max(h->n, 1) * 3)) != 0) return rc;
-    if (h->n > 0) LAUNCH(k_positions_out, cdiv(h->n, 256), 256, h->n, h->cur, h->d_tmp);
+    if ((rc = ensure_tmp(h, (size_t)std::max(std::max(h->n, n), 1) * 3)) != 0) return rc;
+    if (slab) CU(cudaMemcpyAsync(h->d_tmp, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    const int nown = h->dp.own_end - h->dp.own_begin;
+    if (nown > 0) LAUNCH(k_positions_out, cdiv(nown, 256), 256, h->dp.own_begin, nown, h->cur, h->d_tmp);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(xyz, h->d_tmp, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -709,15 +754,18 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
         src ^= 1;
     }
     h->sorted_buf = src;
-    if (h->prm.strict) LAUNCH(k_cell_order_fix, cdiv(n, 128), 128, h->keys[src], h->vals[src], h->cur.ID, n);
+    // in-cell order = ascending original index: the reference's bucket order (strict mode), and the canonical order that
+    // makes both sides of a slab face hold the shared plane identically (slab mode; reserved[1] forces it on one GPU)
+    if (h->prm.strict || h->dp.slab_on || h->prm.reserved[1])
+        LAUNCH(k_cell_order_fix, cdiv(n, 128), 128, h->keys[src], h->vals[src], h->cur.ID, n, (uint32_t)h->dp.num_cells);
     if (gt) gt->end_group(KG_SORT);
     return SPHSM_OK;
 }
 
 // fuse_goal: 0 = plain gather; 1 / 2 = gather + goal / predicted / corrected velocity (2 also stores GOAL and PV)
-static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal) {
+static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool bounds_done = false) {
     const int n = h->n, src = h->sorted_buf;
-    LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
+    if (!bounds_done) LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
     if (fuse_goal) {
         if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm);
         else LAUNCH(k_reorder_goal<false>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm);
@@ -752,30 +800,56 @@ static int ensure_slot_of(sphsm_handle *h) {
     return SPHSM_OK;
 }
 
-static int rest_moments(sphsm_handle *h) {
-    const int n = h->n, B = h->red_blocks;
-    LAUNCH(k_rest_pass1, B, 256, n, h->cur.P, h->cur.O, h->partial);
+// sums over particles end in h->totals; in slab mode the host combines them across ranks (ncclAllReduce) between parts
+static int comm_allreduce(sphsm_handle *h, int count);
+
+// the sums run BEFORE the gather, over the unsorted arrays: in slab mode that extent includes the message regions
+static DevParams moment_params(sphsm_handle *h) {
+    DevParams d = h->dp;
+    if (h->mom_n) d.n = h->mom_n;
+    return d;
+}
+static int rest_part1(sphsm_handle *h) {
+    const int B = h->red_blocks;
+    LAUNCH(k_rest_pass1, B, 256, moment_params(h), h->cur.P, h->cur.O, h->partial);
     LAUNCH(k_sum_partials_par, 5, 256, h->partial, B, 5, h->totals);
+    return SPHSM_OK;
+}
+static int rest_part2(sphsm_handle *h) {
+    const int B = h->red_blocks;
     LAUNCH(k_rest_finalize1, 1, 1, h->totals, h->sm);
-    LAUNCH(k_rest_pass2, dim3(B, 10), 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
+    LAUNCH(k_rest_pass2, dim3(B, 10), 256, moment_params(h), h->cur.P, h->cur.O, h->sm, h->partial);
     for (int r = 0; r < 10; r++) LAUNCH(k_sum_partials_par, 9, 256, h->partial + (size_t)r * B * 9, B, 9, h->totals + r * 9);
+    return SPHSM_OK;
+}
+static int rest_part3(sphsm_handle *h) {
     LAUNCH(k_rest_finalize2, 1, 1, h->totals, h->sm, h->scratch);
     CU(cudaGetLastError());
     h->rest_dirty = false;
     return SPHSM_OK;
 }
+static int moments_part(sphsm_handle *h) {
+    const int B = h->red_blocks;
+    if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, moment_params(h), h->cur.P, h->cur.O, h->sm, h->partial);
+    else LAUNCH(k_moments<3>, B, 256, moment_params(h), h->cur.P, h->cur.O, h->sm, h->partial);
+    const int nacc = h->dp.quadratic ? 33 : 15;
+    LAUNCH(k_sum_partials_par, nacc, 256, h->partial, B, nacc, h->totals);
+    return SPHSM_OK;
+}
+
+static int rest_moments(sphsm_handle *h) {
+    int rc;
+    if ((rc = rest_part1(h)) != 0 || (rc = comm_allreduce(h, 5)) != 0) return rc;
+    if ((rc = rest_part2(h)) != 0 || (rc = comm_allreduce(h, 90)) != 0) return rc;
+    return rest_part3(h);
+}
 
 // calculate_corrected_velocity
 // the fast path's shape-matching transform of this step: moment sums (any slot order) + the single-thread solve
 static int sm_transform_fast(sphsm_handle *h) {
-    const int n = h->n;
     int rc;
     if (h->rest_dirty && (rc = rest_moments(h)) != 0) return rc;
-    const int B = h->red_blocks;
-    if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
-    else LAUNCH(k_moments<3>, B, 256, n, h->cur.P, h->cur.O, h->sm, h->partial);
-    const int nacc = h->dp.quadratic ? 33 : 15;
-    LAUNCH(k_sum_partials_par, nacc, 256, h->partial, B, nacc, h->totals);
+    if ((rc = moments_part(h)) != 0 || (rc = comm_allreduce(h, h->dp.quadratic ? 33 : 15)) != 0) return rc;
     LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
     return SPHSM_OK;
 }
@@ -872,7 +946,7 @@ static int fused_step(sphsm_handle *h) {
         LAUNCH(k_pass_a2, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
         gt.end_group(KG_PASS_A);
         if (diag) LAUNCH(k_pass_b2<true>, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b2<false>, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b2<false>, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);  // single GPU: own range = [0, n)
     }
     std::swap(h->cur.P, h->alt.P);
     gt.end_group(KG_PASS_B);
@@ -900,10 +974,21 @@ static int timed_staged_step(sphsm_handle *h) {
     return SPHSM_OK;
 }
 
+static int mg_step_nccl(sphsm_handle *h);  // the slab step (below)
+
 extern "C" int sphsm_step(sphsm_handle *h, int nsteps) {
     if (!h || nsteps < 0) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
+    if (h->comm_mode == 2) return fail(h, SPHSM_ERR_COMM, "a local group steps through sphsm_step_group");
     CU(cudaEventRecord(h->ev_step0, h->stream));
+    if (h->comm_mode == 1) {
+        for (int s = 0; s < nsteps; s++) {
+            int rc = mg_step_nccl(h);
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(h->ev_step1, h->stream));
+        return SPHSM_OK;
+    }
     for (int s = 0; s < nsteps; s++) {
         int rc;
         if (h->stage_timing) rc = h->prm.strict ? timed_staged_step<true>(h) : timed_staged_step<false>(h);
@@ -947,6 +1032,7 @@ extern "C" int sphsm_profile_step(sphsm_handle *h, int nsteps, float out_ms[SPHS
     h->profiling = true;
     int rc = SPHSM_OK;
     for (int s = 0; s < nsteps && rc == SPHSM_OK; s++) {
+        if (h->comm_mode == 1) { rc = mg_step_nccl(h); continue; }
         rc = h->prm.strict ? fused_step<true>(h) : fused_step<false>(h);
         if (rc == SPHSM_OK) h->total_steps++;
     }
@@ -1057,7 +1143,379 @@ extern "C" int sphsm_get_sm_transform(sphsm_handle *h, float cm[3], float ocm[3]
 }
 
 // ---------------------------------------------------------------------------------------------------
-// multi-GPU entry points live in sphsm_comm.cuh once the slab layer is built; until then they report so.
-extern "C" int sphsm_comm_unique_id(void *) { return fail(nullptr, SPHSM_ERR_COMM, "multi-GPU layer not built yet"); }
-extern "C" int sphsm_comm_init(sphsm_handle *h, int, int, const void *) { return fail(h, SPHSM_ERR_COMM, "multi-GPU layer not built yet"); }
-extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int, int) { return fail(h, SPHSM_ERR_COMM, "multi-GPU layer not built yet"); }
+// multi-GPU slab layer, host side.  NCCL is resolved at run time (dlopen), so single-GPU hosts need no NCCL.
+typedef struct { char internal[128]; } nccl_unique_id;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(nccl_unique_id *) = nullptr;
+    int (*CommInitRank)(void **, int, nccl_unique_id, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+enum { NCCL_CHAR = 0, NCCL_FLOAT = 7, NCCL_DOUBLE = 8, NCCL_SUM = 0 };  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+static int load_nccl(sphsm_handle *h) {
+    if (g_nccl.lib) return SPHSM_OK;
+    const char *names[] = {getenv("SPHSM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *nm : names)
+        if (nm && (lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    if (!lib) return fail(h, SPHSM_ERR_COMM, "libnccl.so.2 not found (set SPHSM_NCCL_LIB)");
+    bool ok = true;
+    auto sym = [&](const char *nm) { void *f = dlsym(lib, nm); if (!f) ok = false; return f; };
+    g_nccl.GetUniqueId = (int (*)(nccl_unique_id *))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, nccl_unique_id, int))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void *))sym("ncclCommDestroy");
+    g_nccl.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))sym("ncclSend");
+    g_nccl.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))sym("ncclRecv");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))sym("ncclAllReduce");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+    if (!ok) return fail(h, SPHSM_ERR_COMM, "libnccl is missing a required entry point");
+    g_nccl.lib = lib;
+    g_nccl_destroy = g_nccl.CommDestroy;
+    return SPHSM_OK;
+}
+#define NC(call)                                                                                        \
+    do {                                                                                                \
+        int r_ = (call);                                                                                \
+        if (r_ != 0) {                                                                                  \
+            std::string m_ = std::string(#call) + " failed: " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+            if (h) h->err = m_; else g_create_error = m_;                                               \
+            return SPHSM_ERR_COMM;                                                                      \
+        }                                                                                               \
+    } while (0)
+
+static int comm_alloc(sphsm_handle *h) {
+    if (h->msg_send[0]) return SPHSM_OK;
+    const int cap = h->send_cap;  // fixed at create (array room was allocated for it)
+    for (int k = 0; k < 2; k++) {
+        CU(cudaMalloc(&h->msg_send[k], msg_bytes(cap)));
+        CU(cudaMalloc(&h->msg_recv[k], msg_bytes(cap)));
+        CU(cudaMemset(h->msg_send[k], 0, 16));
+        CU(cudaMemset(h->msg_recv[k], 0, 16));
+    }
+    CU(cudaMalloc(&h->d_err, 4 * sizeof(int)));
+    CU(cudaMemset(h->d_err, 0, 4 * sizeof(int)));
+    CU(cudaMalloc(&h->d_meta, 8 * sizeof(int)));
+    CU(cudaMallocHost(&h->h_meta, 8 * sizeof(int)));
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_comm_unique_id(void *id128) {
+    sphsm_handle *h = nullptr;
+    if (!id128) return SPHSM_ERR_INVALID;
+    int rc = load_nccl(nullptr);
+    if (rc) return rc;
+    nccl_unique_id id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_comm_init(sphsm_handle *h, int nranks, int rank, const void *id128) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return SPHSM_ERR_INVALID;
+    if (h->prm.slab_axis < 0) return fail(h, SPHSM_ERR_INVALID, "create the handle with params.slab_axis = 0, 1 or 2 for multi-GPU");
+    if (h->prm.strict) return fail(h, SPHSM_ERR_INVALID, "strict mode is single-GPU only");
+    CU(cudaSetDevice(h->prm.device));
+    int rc = load_nccl(h);
+    if (rc) return rc;
+    nccl_unique_id id;
+    memcpy(&id, id128, sizeof id);
+    NC(g_nccl.CommInitRank(&h->nccl_comm, nranks, id, rank));
+    h->comm_mode = 1; h->nranks = nranks; h->rank = rank;
+    return comm_alloc(h);
+}
+
+extern "C" int sphsm_comm_init_local(sphsm_handle **hs, int nranks) {
+    if (!hs || nranks < 1) return SPHSM_ERR_INVALID;
+    for (int r = 0; r < nranks; r++) {
+        sphsm_handle *h = hs[r];
+        if (!h) return SPHSM_ERR_INVALID;
+        if (h->prm.slab_axis < 0) return fail(h, SPHSM_ERR_INVALID, "create the handle with params.slab_axis = 0, 1 or 2 for multi-GPU");
+        if (h->prm.strict) return fail(h, SPHSM_ERR_INVALID, "strict mode is single-GPU only");
+        if (h->prm.device != hs[0]->prm.device || h->prm.capacity != hs[0]->prm.capacity)
+            return fail(h, SPHSM_ERR_INVALID, "a local group shares one device and one capacity");
+        CU(cudaSetDevice(h->prm.device));
+        h->comm_mode = 2; h->nranks = nranks; h->rank = r;
+        int rc = comm_alloc(h);
+        if (rc) return rc;
+    }
+    return SPHSM_OK;
+}
+
+// read the plane boundaries back (one 32-byte copy + stream sync) and set n / owned range from them
+static int slab_meta(sphsm_handle *h) {
+    const DevParams &d = h->dp;
+    LAUNCH(k_mg_meta, 1, 32, h->cell_start, d.num_cells, d.ga * d.gb, d.gcl, h->d_err, h->d_meta);
+    CU(cudaMemcpyAsync(h->h_meta, h->d_meta, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const int *m = h->h_meta;
+    if (m[5]) return fail(h, SPHSM_ERR_COMM, "a particle crossed more than one cell plane in one step (or left the slab window)");
+    if (m[6]) return fail(h, SPHSM_ERR_COMM, "halo message overflow: raise params.reserved[0] (halo capacity)");
+    h->n = m[0];
+    h->dp.n = m[0];
+    h->dp.own_begin = m[1];
+    h->b2 = m[2];
+    h->b3 = m[3];
+    h->dp.own_end = m[4];
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
+    if (!h) return SPHSM_ERR_INVALID;
+    if (!h->comm_mode) return fail(h, SPHSM_ERR_COMM, "sphsm_comm_init first");
+    if (cell_lo < 0 || cell_hi > h->dp.gc || cell_hi - cell_lo < 1) return fail(h, SPHSM_ERR_INVALID, "slab must hold at least one cell plane of the grid");
+    CU(cudaSetDevice(h->prm.device));
+    DevParams &d = h->dp;
+    d.slab_lo = cell_lo; d.slab_hi = cell_hi;
+    d.c_off = cell_lo - 1; d.gcl = cell_hi - cell_lo + 2;
+    d.num_cells = d.ga * d.gb * d.gcl;
+    d.slab_on = 1;
+    int rc;
+    if ((rc = setup_grid_buffers(h)) != 0) return rc;
+    // keep only the owned planes: dead entries sort into the limbo bucket and fall off the end
+    if (h->n > 0) {
+        d.own_begin = 0; d.own_end = h->n;
+        LAUNCH(k_mg_filter, cdiv(h->n, 256), 256, h->dp, h->cur);
+        h->inter_live = true;
+        if ((rc = build_grid(h, nullptr)) != 0) return rc;
+        if ((rc = slab_meta(h)) != 0) return rc;
+    }
+    h->grid_valid = false;
+    h->slab_applied = true;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_comm_info(sphsm_handle *h, int out[8]) {
+    if (!h || !out) return SPHSM_ERR_INVALID;
+    out[0] = h->comm_mode; out[1] = h->nranks; out[2] = h->rank; out[3] = h->n;
+    out[4] = h->dp.own_begin; out[5] = h->dp.own_end; out[6] = h->send_cap; out[7] = h->dp.slab_on;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int cap, int *count) {
+    if (!h || !ids || !xyz || !count || cap < 0) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    const int first = h->dp.own_begin, nown = h->dp.own_end - h->dp.own_begin;
+    *count = nown;
+    if (nown > cap) return fail(h, SPHSM_ERR_CAPACITY, "output arrays smaller than the number of owned particles");
+    if (nown == 0) return SPHSM_OK;
+    int rc;
+    if ((rc = ensure_tmp(h, (size_t)nown * 3)) != 0 || (rc = ensure_itmp(h, (size_t)nown)) != 0) return rc;
+    LAUNCH(k_mg_owned_out, cdiv(nown, 256), 256, first, nown, h->cur, h->d_itmp, h->d_tmp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ids, h->d_itmp, (size_t)nown * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(xyz, h->d_tmp, (size_t)nown * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SPHSM_OK;
+}
+
+// ---- collectives: NCCL (one process per GPU) --------------------------------------------------------------------
+static int comm_allreduce(sphsm_handle *h, int count) {
+    if (h->comm_mode != 1 || h->nranks == 1) return SPHSM_OK;  // single GPU; the local group sums between phases
+    NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm, h->stream));
+    return SPHSM_OK;
+}
+static int nccl_exchange1(sphsm_handle *h) {
+    const size_t bytes = msg_bytes(h->send_cap);
+    NC(g_nccl.GroupStart());
+    if (h->rank > 0) {
+        NC(g_nccl.Send(h->msg_send[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->msg_recv[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
+    }
+    if (h->rank < h->nranks - 1) {
+        NC(g_nccl.Send(h->msg_send[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->msg_recv[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return SPHSM_OK;
+}
+// boundary planes' pass-A results: V = (inter_vel, m/dens) and S = (pres, Vm), contiguous slot ranges on both sides
+static int nccl_exchange2(sphsm_handle *h) {
+    const int ob = h->dp.own_begin, oe = h->dp.own_end, n = h->n;
+    NC(g_nccl.GroupStart());
+    if (h->rank > 0) {
+        NC(g_nccl.Send(h->cur.V + ob, (size_t)(h->b2 - ob) * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Send(h->cur.S + ob, (size_t)(h->b2 - ob) * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->cur.V, (size_t)ob * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->cur.S, (size_t)ob * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
+    }
+    if (h->rank < h->nranks - 1) {
+        NC(g_nccl.Send(h->cur.V + h->b3, (size_t)(oe - h->b3) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Send(h->cur.S + h->b3, (size_t)(oe - h->b3) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->cur.V + oe, (size_t)(n - oe) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->cur.S + oe, (size_t)(n - oe) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return SPHSM_OK;
+}
+
+// ---- the slab step as phases; every phase ends in the collective named by *coll ----------------------------------------
+enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE };
+static const int MG_PHASES = 6;
+
+static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
+    const bool diag = h->prm.diagnostics != 0;
+    const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
+    int rc;
+    *coll = COLL_NONE; *count = 0;
+    switch (phase) {
+        case 0: {  // classify + pack
+            if (h->profiling) h->gt = new GroupTimer(h);
+            CU(cudaMemsetAsync(h->msg_send[0], 0, 16, h->stream));
+            CU(cudaMemsetAsync(h->msg_send[1], 0, 16, h->stream));
+            if (h->n > 0)
+                LAUNCH(k_mg_classify, cdiv(h->n, 256), 256, h->dp, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_send[0], h->send_cap),
+                       msg_view(h->msg_send[1], h->send_cap), h->send_cap, h->d_err);
+            if (h->gt) h->gt->end_group(KG_OTHER);
+            *coll = COLL_EXCH1;
+            return SPHSM_OK;
+        }
+        case 1: {  // unpack arrivals, hash + sort everything, cell table, plane boundaries
+            const int n0 = h->n, cap = h->send_cap;
+            if (n0 + 2 * cap > h->alloc_n) return fail(h, SPHSM_ERR_CAPACITY, "capacity too small for the halo arrivals");
+            LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, n0, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_recv[0], cap),
+                   msg_view(h->msg_recv[1], cap), cap);
+            h->n = n0 + 2 * cap;
+            h->dp.n = h->n;
+            h->mom_n = h->n;
+            if (h->gt) h->gt->end_group(KG_OTHER);
+            if ((rc = grid_sort(h, h->gt)) != 0) return rc;
+            LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
+            if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
+            if (h->gt) h->gt->end_group(KG_GRID);
+            if (h->rest_dirty) {
+                if ((rc = rest_part1(h)) != 0) return rc;
+                *coll = COLL_ALLREDUCE; *count = 5;
+            }
+            return SPHSM_OK;
+        }
+        case 2:
+            if (h->rest_dirty) {
+                if ((rc = rest_part2(h)) != 0) return rc;
+                *coll = COLL_ALLREDUCE; *count = 90;
+            }
+            return SPHSM_OK;
+        case 3:
+            if (h->rest_dirty && (rc = rest_part3(h)) != 0) return rc;
+            if ((rc = moments_part(h)) != 0) return rc;
+            *coll = COLL_ALLREDUCE; *count = h->dp.quadratic ? 33 : 15;
+            return SPHSM_OK;
+        case 4: {  // solve, gather + stage 2, pass A
+            if (memcmp(&h->dp, &h->dp_uploaded, sizeof(DevParams)) != 0) {
+                h->dp_uploaded = h->dp;
+                CU(cudaMemcpyAsync(h->d_dp, &h->dp_uploaded, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
+            }
+            LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
+            h->mom_n = 0;
+            if (h->gt) h->gt->end_group(KG_MOMENTS);
+            if (h->n > 0 && (rc = grid_finish(h, h->gt, diag ? 2 : 1, true)) != 0) return rc;
+            const int nown = h->dp.own_end - h->dp.own_begin;
+            if (nown > 0) LAUNCH(k_pass_a2, cdiv(nown, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+            if (h->gt) h->gt->end_group(KG_PASS_A);
+            *coll = COLL_EXCH2;
+            return SPHSM_OK;
+        }
+        case 5: {  // pass B on the owned slots
+            if (h->gt) h->gt->end_group(KG_OTHER);  // exchange 2
+            const int nown = h->dp.own_end - h->dp.own_begin;
+            if (nown > 0) {
+                if (diag) LAUNCH(k_pass_b2<true>, cdiv(nown, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+                else LAUNCH(k_pass_b2<false>, cdiv(nown, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+            }
+            std::swap(h->cur.P, h->alt.P);
+            if (h->gt) {
+                h->gt->end_group(KG_PASS_B);
+                h->gt->finish();
+                delete h->gt;
+                h->gt = nullptr;
+            }
+            CU(cudaGetLastError());
+            h->grid_valid = false;
+            h->inter_live = false;
+            h->total_steps++;
+            *coll = COLL_DONE;
+            return SPHSM_OK;
+        }
+    }
+    return fail(h, SPHSM_ERR_INVALID, "bad phase");
+}
+
+static int mg_check(sphsm_handle *h) {
+    if (!h->slab_applied) return fail(h, SPHSM_ERR_COMM, "sphsm_comm_set_slab must be applied after the particle set is uploaded");
+    if (h->stage_timing) return fail(h, SPHSM_ERR_INVALID, "stage timing is single-GPU only");
+    return SPHSM_OK;
+}
+
+static int mg_step_nccl(sphsm_handle *h) {
+    int rc, coll, count;
+    if ((rc = mg_check(h)) != 0) return rc;
+    for (int ph = 0; ph < MG_PHASES; ph++) {
+        if ((rc = mg_phase(h, ph, &coll, &count)) != 0) return rc;
+        if (coll == COLL_EXCH1) rc = nccl_exchange1(h);
+        else if (coll == COLL_ALLREDUCE) rc = comm_allreduce(h, count);
+        else if (coll == COLL_EXCH2) rc = nccl_exchange2(h);
+        if (rc) return rc;
+    }
+    return SPHSM_OK;
+}
+
+// virtual ranks: the same phases in lockstep over handles that share one device; collectives are device copies
+extern "C" int sphsm_step_group(sphsm_handle **hs, int nranks, int nsteps) {
+    if (!hs || nranks < 1 || nsteps < 0) return SPHSM_ERR_INVALID;
+    for (int r = 0; r < nranks; r++) {
+        sphsm_handle *h = hs[r];
+        if (!h || h->comm_mode != 2 || h->nranks != nranks || h->rank != r) return fail(h, SPHSM_ERR_COMM, "not the local group made by sphsm_comm_init_local");
+        int rc = mg_check(h);
+        if (rc) return rc;
+    }
+    sphsm_handle *h = hs[0];
+    CU(cudaSetDevice(h->prm.device));
+    std::vector<int> coll(nranks), count(nranks);
+    std::vector<double> sum(128), part(128);
+    for (int s = 0; s < nsteps; s++) {
+        for (int ph = 0; ph < MG_PHASES; ph++) {
+            for (int r = 0; r < nranks; r++) {
+                int rc = mg_phase(hs[r], ph, &coll[r], &count[r]);
+                if (rc) return rc;
+                if (coll[r] != coll[0] || count[r] != count[0]) return fail(hs[r], SPHSM_ERR_COMM, "ranks disagree on the phase program");
+            }
+            for (int r = 0; r < nranks; r++) CU(cudaStreamSynchronize(hs[r]->stream));
+            if (coll[0] == COLL_EXCH1) {
+                const size_t bytes = msg_bytes(h->send_cap);
+                for (int r = 0; r < nranks; r++) {
+                    if (r > 0) CU(cudaMemcpy(hs[r]->msg_recv[0], hs[r - 1]->msg_send[1], bytes, cudaMemcpyDeviceToDevice));
+                    if (r < nranks - 1) CU(cudaMemcpy(hs[r]->msg_recv[1], hs[r + 1]->msg_send[0], bytes, cudaMemcpyDeviceToDevice));
+                }
+            } else if (coll[0] == COLL_ALLREDUCE) {
+                const int c = count[0];
+                std::fill(sum.begin(), sum.end(), 0.0);
+                for (int r = 0; r < nranks; r++) {
+                    CU(cudaMemcpy(part.data(), hs[r]->totals, c * sizeof(double), cudaMemcpyDeviceToHost));
+                    for (int k = 0; k < c; k++) sum[k] += part[k];
+                }
+                for (int r = 0; r < nranks; r++) CU(cudaMemcpy(hs[r]->totals, sum.data(), c * sizeof(double), cudaMemcpyHostToDevice));
+            } else if (coll[0] == COLL_EXCH2) {
+                for (int r = 0; r + 1 < nranks; r++) {  // face between rank r (left) and rank r + 1 (right)
+                    sphsm_handle *a = hs[r], *b = hs[r + 1];
+                    const int na = a->dp.own_end - a->b3, nb_halo = b->dp.own_begin;       // a's last owned plane -> b's left halo
+                    const int nb = b->b2 - b->dp.own_begin, na_halo = a->n - a->dp.own_end;  // b's first owned plane -> a's right halo
+                    if (na != nb_halo || nb != na_halo) return fail(a, SPHSM_ERR_COMM, "boundary plane populations differ across a slab face");
+                    CU(cudaMemcpy(b->cur.V, a->cur.V + a->b3, (size_t)na * sizeof(float4), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(b->cur.S, a->cur.S + a->b3, (size_t)na * sizeof(float2), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(a->cur.V + a->dp.own_end, b->cur.V + b->dp.own_begin, (size_t)nb * sizeof(float4), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(a->cur.S + a->dp.own_end, b->cur.S + b->dp.own_begin, (size_t)nb * sizeof(float2), cudaMemcpyDeviceToDevice));
+                }
+            }
+        }
+    }
+    return SPHSM_OK;
+}

@@ -78,8 +78,8 @@ __device__ __forceinline__ void sweep_two_phase(const DevParams &p, const int *_
 __global__ void __launch_bounds__(PT) k_pass_a2(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 const int *__restrict__ cell_start) {
     __shared__ int s_list[LIST_K * PT];
-    const int i = blockIdx.x * PT + threadIdx.x;
-    if (i >= p.n) return;
+    const int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
+    if (i >= p.own_end) return;
     const float4 pi = a.P[i];
     const float4 ci = a.C[i];
     const float4 *__restrict__ P = a.P;
@@ -130,8 +130,8 @@ template <bool DIAG>
 __global__ void __launch_bounds__(PT) k_pass_b2(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 float4 *__restrict__ Pout, const int *__restrict__ cell_start) {
     __shared__ int s_list[LIST_K * PT];
-    const int i = blockIdx.x * PT + threadIdx.x;
-    if (i >= p.n) return;
+    const int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
+    if (i >= p.own_end) return;
     const float4 pi = a.P[i];
     const float4 vi = a.V[i];
     float4 e4 = a.E[i];

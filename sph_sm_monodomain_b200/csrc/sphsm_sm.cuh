@@ -11,6 +11,7 @@
 // 653-667) and m3Matrix::{polarDecomposition,eigenDecomposition,jacobiRotate,invert,determinant} (Math3D/
 // m3Matrix.cpp:3-113, m3Matrix.h:288-318), m9Matrix::invert (Math3D/m9Matrix.cpp:10-102).
 #pragma once
+#include "sphsm_comm.cuh"
 #include "sphsm_types.cuh"
 
 namespace sphsm {
@@ -224,10 +225,15 @@ __device__ __forceinline__ void block_reduce_store(double *acc, double *out) {
 }
 
 // rest pass 1: [0] sum m', [1] sum m, [2..4] sum m' X      (cpp:244-251; fixed particles weigh x100 here, Q4)
-__global__ void __launch_bounds__(256) k_rest_pass1(int n, const float4 *__restrict__ P, const float4 *__restrict__ O, double *partial) {
+// In slab mode (p.slab_on) every sum covers the particles this rank owns; the partial sums are allreduced by the host.
+__global__ void __launch_bounds__(256) k_rest_pass1(const __grid_constant__ DevParams p, const float4 *__restrict__ P, const float4 *__restrict__ O,
+                                                    double *partial) {
+    const int n = p.n;
     double acc[5] = {0, 0, 0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float m = P[i].w;
+        const float4 q4 = P[i];
+        if (p.slab_on && !slab_owned(p, q4)) continue;
+        float m = q4.w;
         float4 o = O[i];
         float mf = __float_as_int(o.w) ? __fmul_rn(m, 100.0f) : m;
         acc[0] += mf; acc[1] += m;
@@ -236,12 +242,16 @@ __global__ void __launch_bounds__(256) k_rest_pass1(int n, const float4 *__restr
     block_reduce_store<5>(acc, partial + (size_t)blockIdx.x * 5);
 }
 // rest pass 2, blockIdx.y = row r of [ A9qq (rows 0..8) ; sum m q9 (row 9) ]: 9 doubles per block
-__global__ void __launch_bounds__(256) k_rest_pass2(int n, const float4 *__restrict__ P, const float4 *__restrict__ O, const SmState *sm, double *partial) {
+__global__ void __launch_bounds__(256) k_rest_pass2(const __grid_constant__ DevParams p, const float4 *__restrict__ P, const float4 *__restrict__ O,
+                                                    const SmState *sm, double *partial) {
+    const int n = p.n;
     const int row = blockIdx.y;
     const float ox = sm->ocm[0], oy = sm->ocm[1], oz = sm->ocm[2];
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float m = P[i].w;
+        const float4 q4 = P[i];
+        if (p.slab_on && !slab_owned(p, q4)) continue;
+        float m = q4.w;
         float4 o = O[i];
         float q9[9];
         make_q9(__fsub_rn(o.x, ox), __fsub_rn(o.y, oy), __fsub_rn(o.z, oz), q9);
@@ -290,7 +300,9 @@ __global__ void k_rest_finalize2(const double *__restrict__ tot, SmState *sm, fl
 
 // per-step sums: [0..2] sum m' x, [3..5] sum m x, [6 + a*NB + b] sum m x_a q9_b   (NB = 3 linear, 9 quadratic)
 template <int NB>
-__global__ void __launch_bounds__(256) k_moments(int n, const float4 *__restrict__ P, const float4 *__restrict__ O, const SmState *sm, double *partial) {
+__global__ void __launch_bounds__(256) k_moments(const __grid_constant__ DevParams p, const float4 *__restrict__ P, const float4 *__restrict__ O,
+                                                 const SmState *sm, double *partial) {
+    const int n = p.n;
     constexpr int NACC = 6 + 3 * NB;
     const float ox = sm->ocm[0], oy = sm->ocm[1], oz = sm->ocm[2];
     double acc[NACC];
@@ -298,6 +310,7 @@ __global__ void __launch_bounds__(256) k_moments(int n, const float4 *__restrict
     for (int k = 0; k < NACC; k++) acc[k] = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 q4 = P[i];
+        if (p.slab_on && !slab_owned(p, q4)) continue;
         float4 o = O[i];
         float m = q4.w;
         float mf = __float_as_int(o.w) ? __fmul_rn(m, 100.0f) : m;

@@ -191,10 +191,11 @@ k_radix_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin,
 
 // strict mode: the reference's bucket order is ascending particle index (push_back order, cpp:207-212).
 // One thread per sorted slot that starts a cell: insertion-sort that cell's source slots by original index.
-__global__ void k_cell_order_fix(const uint32_t *__restrict__ keys, uint32_t *vals, const int *__restrict__ id_src, int n) {
+__global__ void k_cell_order_fix(const uint32_t *__restrict__ keys, uint32_t *vals, const int *__restrict__ id_src, int n, uint32_t num_cells) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t k = keys[s];
+    if (k >= num_cells) return;  // the limbo bucket (outside the grid / dead entries) has no order to keep
     if (s > 0 && keys[s - 1] == k) return;
     int e = s + 1;
     while (e < n && keys[e] == k) e++;

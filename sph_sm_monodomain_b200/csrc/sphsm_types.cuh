@@ -47,6 +47,8 @@ struct DevParams {
     // slab decomposition (multi-GPU): this rank's grid holds the planes [c_off, c_off + gcl) along perm[2]
     // (owned planes [slab_lo, slab_hi) plus one halo plane per interior side); single GPU: c_off = 0, gcl = gc.
     int c_off, gcl, slab_lo, slab_hi;
+    int slab_on;              // 1: multi-GPU slab mode (sums and outputs cover owned particles only)
+    int own_begin, own_end;   // slot range the neighbour passes compute ([0, n) on a single GPU)
     int zero;  // always 0; read from the global-memory copy of this block to build values ptxas cannot re-materialise
 };
 

@@ -226,6 +226,36 @@ class Sim:
         self._ck(self.lib.sphsm_get_sm_transform(self.h, _fp(cm), _fp(ocm), _fp(x)))
         return cm, ocm, x
 
+    # ---- multi-GPU slab layer (no reference counterpart; include/sphsm_b200.h) ---------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = _capi.load()
+        buf = C.create_string_buffer(128)
+        _capi.check(lib, None, lib.sphsm_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.sphsm_comm_init(self.h, int(nranks), int(rank), buf))
+
+    def set_slab(self, lo, hi):
+        self._ck(self.lib.sphsm_comm_set_slab(self.h, int(lo), int(hi)))
+
+    def comm_info(self):
+        out = np.zeros(8, np.int32)
+        self._ck(self.lib.sphsm_comm_info(self.h, _ip(out)))
+        keys = ("mode", "nranks", "rank", "n_local", "own_begin", "own_end", "halo_capacity", "slab_on")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def download_owned(self):
+        """(ids, positions) of the particles this rank owns (all particles on a single GPU)."""
+        cap = max(self.n, 1)
+        ids = np.zeros(cap, np.int32)
+        xyz = np.zeros((cap, 3), np.float32)
+        cnt = C.c_int()
+        self._ck(self.lib.sphsm_download_owned(self.h, _ip(ids), _fp(xyz), cap, C.byref(cnt)))
+        return ids[: cnt.value].copy(), xyz[: cnt.value].copy()
+
     # ---- timers / counters --------------------------------------------------------------------------------
     def enable_stage_timing(self, on=True):
         self._ck(self.lib.sphsm_enable_stage_timing(self.h, int(on)))
@@ -263,3 +293,31 @@ class Sim:
         line = ";".join(f"{x:g}" for x in head) + ";" + ";".join(f"{x:g}" for x in tail)
         print(line)
         return line
+
+
+class LocalGroup:
+    """Virtual ranks on ONE device (sphsm_comm_init_local / sphsm_step_group): the slab logic of the multi-GPU path with
+    device copies in place of NCCL.  Used by the GPU tests; production runs one process per GPU (bench.py)."""
+
+    def __init__(self, sims):
+        self.sims = list(sims)
+        self.lib = self.sims[0].lib
+        self._arr = (C.c_void_p * len(self.sims))(*[s.h for s in self.sims])
+        _capi.check(self.lib, self.sims[0].h, self.lib.sphsm_comm_init_local(self._arr, len(self.sims)))
+
+    def step(self, nsteps=1):
+        rc = self.lib.sphsm_step_group(self._arr, len(self.sims), int(nsteps))
+        if rc:
+            msgs = [self.lib.sphsm_last_error(s.h).decode() for s in self.sims]
+            raise SphsmError(f"sphsm_step_group failed ({rc}): {msgs}")
+
+    def gather_positions(self, n_global):
+        """Owned particles of every virtual rank assembled by original id; also returns the owner rank per particle."""
+        pos = np.full((n_global, 3), np.nan, np.float32)
+        owner = np.full(n_global, -1, np.int32)
+        for r, s in enumerate(self.sims):
+            ids, xyz = s.download_owned()
+            assert (owner[ids] == -1).all(), "a particle is owned by two ranks"
+            pos[ids] = xyz
+            owner[ids] = r
+        return pos, owner

@@ -183,13 +183,31 @@ def run_ours(args, wl, rank, world_size, local_rank):
     pos, world, fixed, stim = make_lattice(wl["dims"])
     n_total = len(pos)
     if world_size > 1:
-        raise SystemExit("multi-GPU slab layer not built yet")
-    sim = Sim(capacity=n_total, world=world, device=device, diagnostics=False)
+        # slab decomposition along the longest axis: every rank uploads the global set, then keeps the
+        # cell planes the balanced partition gives it; halos / migrants travel by ncclSend/ncclRecv inside sphsm_step
+        from sph_sm_monodomain_b200 import slabs
+
+        axis = slabs.slab_axis_for(world)
+        npl = slabs.num_planes(world, axis)
+        parts = slabs.partition_planes(slabs.plane_histogram(pos, axis, npl), world_size)
+        sim = Sim(capacity=n_total, world=world, device=device, diagnostics=False, slab_axis=axis)
+    else:
+        sim = Sim(capacity=n_total, world=world, device=device, diagnostics=False)
     sim.Init_Fluid(pos)
     sim.set_masks(fixed, stim)
     if wl["quadratic"]:
         sim.flip_quadratic()
-    n_local = sim.n
+    if world_size > 1:
+        ident = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(Sim.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, 0)
+        sim.comm_init(world_size, rank, bytes(ident.cpu().numpy().tobytes()))
+        sim.set_slab(*parts[rank])
+        info = sim.comm_info()
+        n_local = info["own_end"] - info["own_begin"]
+    else:
+        n_local = sim.n
 
     def barrier():
         if dist is not None:
@@ -222,6 +240,9 @@ def run_ours(args, wl, rank, world_size, local_rank):
     groups = sim.profile_step(prof_steps)
     peak, peak_src = measured_peak_gbs()
     pb_ms = groups[PASS_B_NAME]
+    if world_size > 1:
+        info = sim.comm_info()
+        n_local = info["own_end"] - info["own_begin"]
     achieved = PASS_B_BYTES_PER_PARTICLE * n_local / (pb_ms * 1e-3) / 1e9
     roofline = {"kernel": "k_pass_b (fused cell model + force + Laplacian + integration)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -239,17 +260,25 @@ def run_ours(args, wl, rank, world_size, local_rank):
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------------------
     stim_host = torch.from_numpy(stim.copy()).pin_memory()
-    pos_host = torch.empty((n_local, 3), dtype=torch.float32).pin_memory()
+    own_cap = n_total if world_size == 1 else min(n_total, int(n_local * 1.25) + 65536)  # owned counts drift with migration
+    pos_host = torch.empty((own_cap, 3), dtype=torch.float32).pin_memory()
+    ids_host = torch.empty((own_cap,), dtype=torch.int32).pin_memory()
     lib = sim.lib
-    FP = C.POINTER(C.c_float)
+    FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int)
     stim_ptr = C.cast(stim_host.data_ptr(), FP)
     pos_ptr = C.cast(pos_host.data_ptr(), FP)
+    ids_ptr = C.cast(ids_host.data_ptr(), IP)
+    own_cnt = C.c_int()
     e2e_steps = max(3, min(args.steps, 20))
 
     def e2e_step():
-        _capi.check(lib, sim.h, lib.sphsm_set_masks(sim.h, None, stim_ptr, n_local))    # H2D: 4 B / particle
+        # H2D: the per-particle stimulation array (4 B / particle; every rank holds the global mask, ids are global)
+        _capi.check(lib, sim.h, lib.sphsm_set_masks(sim.h, None, stim_ptr, n_total))
         _capi.check(lib, sim.h, lib.sphsm_step(sim.h, 1))
-        _capi.check(lib, sim.h, lib.sphsm_download_positions(sim.h, pos_ptr, n_local))  # D2H: 12 B / particle
+        if world_size == 1:  # D2H: positions in the caller's order, 12 B / particle
+            _capi.check(lib, sim.h, lib.sphsm_download_positions(sim.h, pos_ptr, n_total))
+        else:                # D2H: (id, position) of the particles this rank owns, 16 B / particle
+            _capi.check(lib, sim.h, lib.sphsm_download_owned(sim.h, ids_ptr, pos_ptr, own_cap, C.byref(own_cnt)))
 
     for _ in range(2):
         e2e_step()
@@ -262,10 +291,15 @@ def run_ours(args, wl, rank, world_size, local_rank):
     te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{device}")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": n_total * e2e_steps / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(4 * n_total),
-           "d2h_bytes_per_step": int(12 * n_total), "steps": e2e_steps,
-           "protocol": "per step: sphsm_set_masks(stim) from pinned host memory -> sphsm_step(1) -> sphsm_download_positions to pinned host memory"}
-    assert np.isfinite(pos_host.numpy()).all()
+    h2d = 4 * n_total * world_size
+    d2h = 12 * n_total if world_size == 1 else 16 * n_total
+    e2e = {"value": n_total * e2e_steps / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+           "protocol": "per step: sphsm_set_masks(stim) from pinned host memory -> sphsm_step(1) -> "
+                       + ("sphsm_download_positions" if world_size == 1 else "sphsm_download_owned (ids + positions of the rank's slab)")
+                       + " to pinned host memory; bytes summed over ranks"}
+    n_read = n_total if world_size == 1 else own_cnt.value
+    assert np.isfinite(pos_host.numpy()[:n_read]).all()
 
     if rank == 0:
         cpu = cpu_reference_rate(wl["quadratic"], 20, 2) if not args.no_cpu_baseline else None

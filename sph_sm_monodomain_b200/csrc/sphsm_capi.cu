@@ -82,6 +82,7 @@ struct sphsm_handle {
     uint8_t *msg_send[2] = {nullptr, nullptr}, *msg_recv[2] = {nullptr, nullptr};  // [0] left neighbour, [1] right neighbour
     int *d_err = nullptr, *d_meta = nullptr, *h_meta = nullptr;
     int b2 = 0, b3 = 0;       // start of the 2nd / of the last owned plane (exchange-2 ranges)
+    int n_global = 0;         // particles uploaded before sphsm_comm_set_slab filtered them (ids are global)
     int mom_n = 0;            // slab step: extent of the PRE-reorder arrays (old slots + both message regions) the moment sums scan
     struct GroupTimer *gt = nullptr;
 };
@@ -679,7 +680,8 @@ extern "C" int sphsm_stim_off(sphsm_handle *h) {
 }
 
 extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const float *stim, int n) {
-    if (!h || n != h->n) return fail(h, SPHSM_ERR_INVALID, "set_masks needs exactly num_particles entries");
+    // slab mode: the arrays are indexed by ORIGINAL (global) id, so they hold the global particle count
+    if (!h || n != (h->dp.slab_on ? h->n_global : h->n)) return fail(h, SPHSM_ERR_INVALID, "set_masks needs exactly num_particles entries");
     if (n == 0 || (!fixed && !stim)) return SPHSM_OK;
     CU(cudaSetDevice(h->prm.device));
     int rc;
@@ -687,8 +689,9 @@ extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const floa
     if ((rc = ensure_itmp(h, (size_t)(n + 3) / 4)) != 0) return rc;
     if (stim) CU(cudaMemcpyAsync(h->d_tmp, stim, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     if (fixed) CU(cudaMemcpyAsync(h->d_itmp, fixed, (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    LAUNCH(k_set_masks, cdiv(n, 256), 256, n, h->cur, fixed ? (const uint8_t *)h->d_itmp : nullptr, stim ? h->d_tmp : nullptr,
-           h->prm.diagnostics);
+    if (h->n > 0)
+        LAUNCH(k_set_masks, cdiv(h->n, 256), 256, h->n, h->cur, fixed ? (const uint8_t *)h->d_itmp : nullptr, stim ? h->d_tmp : nullptr,
+               h->prm.diagnostics);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     if (fixed) h->rest_dirty = true;
@@ -756,8 +759,9 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
     h->sorted_buf = src;
     // in-cell order = ascending original index: the reference's bucket order (strict mode), and the canonical order that
     // makes both sides of a slab face hold the shared plane identically (slab mode; reserved[1] forces it on one GPU)
-    if (h->prm.strict || h->dp.slab_on || h->prm.reserved[1])
-        LAUNCH(k_cell_order_fix, cdiv(n, 128), 128, h->keys[src], h->vals[src], h->cur.ID, n, (uint32_t)h->dp.num_cells);
+    // (the slab step orders only the planes on either side of its faces, once the plane boundaries are known)
+    if (h->prm.strict || h->prm.reserved[1])
+        LAUNCH(k_cell_order_fix, cdiv(n, 128), 128, h->keys[src], h->vals[src], h->cur.ID, n, (uint32_t)h->dp.num_cells, 0, n);
     if (gt) gt->end_group(KG_SORT);
     return SPHSM_OK;
 }
@@ -1275,6 +1279,7 @@ extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
     if (cell_lo < 0 || cell_hi > h->dp.gc || cell_hi - cell_lo < 1) return fail(h, SPHSM_ERR_INVALID, "slab must hold at least one cell plane of the grid");
     CU(cudaSetDevice(h->prm.device));
     DevParams &d = h->dp;
+    if (!d.slab_on) h->n_global = h->n;
     d.slab_lo = cell_lo; d.slab_hi = cell_hi;
     d.c_off = cell_lo - 1; d.gcl = cell_hi - cell_lo + 2;
     d.num_cells = d.ga * d.gb * d.gcl;
@@ -1391,6 +1396,17 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             if ((rc = grid_sort(h, h->gt)) != 0) return rc;
             LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
             if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
+            if (!h->prm.reserved[1] && h->n > 0) {
+                // canonical in-cell order (ascending original id) where two ranks must agree slot by slot: the halo
+                // plane and the owned plane on either side of each face (arrivals were appended in atomic order)
+                const int src = h->sorted_buf, ob = h->dp.own_begin, oe = h->dp.own_end;
+                const bool one = h->b3 <= h->b2;  // slab of one or two planes: the ranges meet
+                const int r0 = 0, c0 = one ? h->n : (has_left ? h->b2 : 0);
+                const int r1 = h->b3, c1 = one ? 0 : (has_right ? h->n - h->b3 : 0);
+                (void)ob; (void)oe;
+                if (c0 > 0) LAUNCH(k_cell_order_fix, cdiv(c0, 128), 128, h->keys[src], h->vals[src], h->cur.ID, h->n, (uint32_t)h->dp.num_cells, r0, c0);
+                if (c1 > 0) LAUNCH(k_cell_order_fix, cdiv(c1, 128), 128, h->keys[src], h->vals[src], h->cur.ID, h->n, (uint32_t)h->dp.num_cells, r1, c1);
+            }
             if (h->gt) h->gt->end_group(KG_GRID);
             if (h->rest_dirty) {
                 if ((rc = rest_part1(h)) != 0) return rc;

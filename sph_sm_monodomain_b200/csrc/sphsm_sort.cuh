@@ -191,8 +191,12 @@ k_radix_pass(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin,
 
 // strict mode: the reference's bucket order is ascending particle index (push_back order, cpp:207-212).
 // One thread per sorted slot that starts a cell: insertion-sort that cell's source slots by original index.
-__global__ void k_cell_order_fix(const uint32_t *__restrict__ keys, uint32_t *vals, const int *__restrict__ id_src, int n, uint32_t num_cells) {
+// Slots [first, first + count) are examined (a cell that STARTS there is ordered completely, wherever it ends).
+__global__ void k_cell_order_fix(const uint32_t *__restrict__ keys, uint32_t *vals, const int *__restrict__ id_src, int n, uint32_t num_cells,
+                                 int first, int count) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    s += first;
     if (s >= n) return;
     uint32_t k = keys[s];
     if (k >= num_cells) return;  // the limbo bucket (outside the grid / dead entries) has no order to keep

@@ -126,9 +126,9 @@ class Sim:
         self._ck(self.lib.sphsm_stim_off(self.h))
 
     def set_masks(self, fixed=None, stim=None):
-        n = self.n
         f = None if fixed is None else np.ascontiguousarray(np.asarray(fixed).astype(np.uint8))
         s = None if stim is None else np.ascontiguousarray(stim, dtype=np.float32)
+        n = len(f) if f is not None else (len(s) if s is not None else self.n)  # slab mode: the GLOBAL count (ids are global)
         self._ck(self.lib.sphsm_set_masks(self.h, None if f is None else f.ctypes.data_as(C.POINTER(C.c_uint8)),
                                           None if s is None else _fp(s), n))
 

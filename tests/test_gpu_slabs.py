@@ -1,10 +1,12 @@
 """GPU (one device): the multi-GPU slab step run as VIRTUAL RANKS (sphsm_comm_init_local / sphsm_step_group — the same
 phases the NCCL path runs, collectives as device copies) against the single-GPU step on the same input.
 
-With the canonical in-cell order (ascending original index, params.reserved[1] on the single-GPU side) every neighbour
-sum visits its candidates in the same order on both sides, so halo / migrant handling is bit-identical; only the
-shape-matching moment sums are combined in a different order (per-rank partial sums added on the host), which moves the
-goal positions by an ulp or so.  Bound: 2e-6 of the field scale after 25 steps; ownership must partition the particles."""
+With the canonical in-cell order everywhere (ascending original index, params.reserved[1]) every neighbour sum visits its
+candidates in the same order on both sides, so halo / migrant handling is bit-identical; only the shape-matching moment
+sums are combined in a different order (per-rank partial sums added on the host), which can move the goal positions by an
+ulp.  Bound: 2e-6 of the field scale after 25 steps.  The production default orders only the planes next to a slab face
+(that is all the exchange needs); interior cells then sum in arrival order and the run differs from the single-GPU one by
+summation-order rounding: bound 1e-5.  Ownership must partition the particles in both modes."""
 import numpy as np
 import pytest
 
@@ -31,8 +33,15 @@ def setup_case(dims, jitter):
     return pos, world, fixed, stim
 
 
+def canonical_everywhere(sim):
+    p = sim.get_params()
+    p.reserved[1] = 1  # in-cell order = ascending original index in EVERY cell
+    sim._ck(sim.lib.sphsm_set_params(sim.h, p))
+
+
+@pytest.mark.parametrize("canonical", [True, False], ids=["canonical", "default"])
 @pytest.mark.parametrize("nranks,quadratic,jitter", [(2, False, 0.0), (3, True, 0.05), (4, False, 0.05)])
-def test_virtual_ranks_match_single_gpu(nranks, quadratic, jitter):
+def test_virtual_ranks_match_single_gpu(nranks, quadratic, jitter, canonical):
     from sph_sm_monodomain_b200 import LocalGroup, Sim
 
     dims = (40, 9, 8)
@@ -40,9 +49,7 @@ def test_virtual_ranks_match_single_gpu(nranks, quadratic, jitter):
     pos, world, fixed, stim = setup_case(dims, jitter)
     n = len(pos)
     single = make(Sim, pos, world, fixed, stim, quadratic)
-    p = single.get_params()
-    p.reserved[1] = 1  # canonical in-cell order on the single-GPU side too
-    single._ck(single.lib.sphsm_set_params(single.h, p))
+    canonical_everywhere(single)
     single.Animation(steps)
     ids1, xyz1 = single.download_owned()
     ref = np.empty((n, 3), np.float32)
@@ -54,6 +61,8 @@ def test_virtual_ranks_match_single_gpu(nranks, quadratic, jitter):
     sims = [make(Sim, pos, world, fixed, stim, quadratic) for _ in range(nranks)]
     grp = LocalGroup(sims)
     for s, (lo, hi) in zip(sims, parts):
+        if canonical:
+            canonical_everywhere(s)  # default: only the planes on either side of a slab face are put in canonical order
         s.set_slab(lo, hi)
     own0 = [s.comm_info() for s in sims]
     assert sum(i["own_end"] - i["own_begin"] for i in own0) == n
@@ -65,7 +74,7 @@ def test_virtual_ranks_match_single_gpu(nranks, quadratic, jitter):
     for r, (lo, hi) in enumerate(parts):
         assert ((pl[owner == r] >= lo - 1) & (pl[owner == r] < hi + 1)).all()
     err = rel_err(got, ref)
-    assert err <= 2e-6, err
+    assert err <= (2e-6 if canonical else 1e-5), err
     infos = [s.comm_info() for s in sims]
     for r, i in enumerate(infos):  # interior ranks carry two halo planes, end ranks one
         halos = (i["own_begin"] > 0) + (i["n_local"] > i["own_end"])

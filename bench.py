@@ -46,6 +46,7 @@ WORKLOADS = {
     "32m": dict(dims=(800, 200, 200), quadratic=False, name="synthetic 32M-particle lattice 800x200x200, monodomain pacing (configs[4])"),
 }
 CPU_SAMPLE_DIMS = (40, 40, 40)  # bounded sample for the CPU legs: 64k particles of the same lattice / SM mode
+CPU_SAMPLE_STEPS = 200          # ~10-15 s of single-thread CPU work at ~1.2e6 particle-steps/s
 
 
 def parse_workload(s):
@@ -75,7 +76,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -152,7 +153,7 @@ def cpu_reference_rate(quadratic, steps, warmup, backend=None):
 def run_reference(args, wl, rank, world_size):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 200))
+    steps = max(1, min(args.steps, 100))  # each "step" of this arm is one CPU step of the bounded sample (~50 ms)
     base = cpu_reference_rate(wl["quadratic"], steps, min(args.warmup, 3))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 3), "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong",
@@ -216,11 +217,14 @@ def run_ours(args, wl, rank, world_size, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput -----------------------------------------------------------------------------
-    sim.Animation(args.warmup)
-    barrier()
-    sim.reset_launch_count()
+    # clocks / throttle reasons are sampled from before the warm-up until after the timed region (a strong-scaled timed
+    # region can be shorter than one nvidia-smi sampling period, so the warm-up steps keep the GPU under the same load)
     sampler = ClockSampler(device)
     sampler.start()
+    prewarm = max(args.warmup, int(0.35 / max(5e-5, 2.5e-10 * n_total / world_size)))  # >= ~0.35 s under load for the sampler
+    sim.Animation(prewarm)
+    barrier()
+    sim.reset_launch_count()
     barrier()
     t0 = time.perf_counter()
     sim.Animation(args.steps)
@@ -302,13 +306,14 @@ def run_ours(args, wl, rank, world_size, local_rank):
     assert np.isfinite(pos_host.numpy()[:n_read]).all()
 
     if rank == 0:
-        cpu = cpu_reference_rate(wl["quadratic"], 20, 2) if not args.no_cpu_baseline else None
+        cpu = cpu_reference_rate(wl["quadratic"], CPU_SAMPLE_STEPS, 2) if not args.no_cpu_baseline else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "particles": n_total, "world": [round(w, 4) for w in world],
                            "shape_matching": "quadratic" if wl["quadratic"] else "linear", "parallelism": f"slab{world_size}",
-                           "l2": "inputs larger than L2 (no flush): %.0f MB of persistent state" % (n_total * 68 / 1e6)},
+                           "l2": "inputs larger than L2 (no flush): %.0f MB of persistent state" % (n_total * 68 / 1e6),
+                           "warmup_steps_run": prewarm},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                 "roofline": roofline}
         if cpu:

@@ -35,21 +35,37 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 // Sweep the stencil rows in the reference's order.  `body(j)` runs for every candidate slot and returns true when the
 // slot must be appended to the in-range list; `drain()` consumes the list.  A row that could overflow the list takes
 // the checked path (dense meshes); lattice-like inputs never do.
+// The bounds of the three rows of a stencil plane are loaded together, one plane AHEAD of the sweep (r01_v3 profile:
+// a third of the stall samples sat on the row-bounds load -> candidate load chain, nine times per particle).
+struct PlaneRows {
+    int s[3], e[3];
+};
+__device__ __forceinline__ void load_plane_rows(const DevParams &p, const int *__restrict__ cell_start, int a_lo, int a_hi, int cb, int c2, PlaneRows &r) {
+    const bool plane_ok = c2 >= p.c_off && c2 < p.c_off + p.gcl;
+    const int base = p.ga * (p.gb * (c2 - p.c_off));
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int b2 = cb + k - 1;
+        const bool ok = plane_ok && b2 >= 0 && b2 < p.gb;
+        const int row = base + p.ga * b2;
+        r.s[k] = ok ? __ldg(cell_start + row + a_lo) : 0;
+        r.e[k] = ok ? __ldg(cell_start + row + a_hi + 1) : 0;
+    }
+}
+
 template <class Body, class Drain>
 __device__ __forceinline__ void sweep_two_phase(const DevParams &p, const int *__restrict__ cell_start, int ca, int cb, int cc,
                                                 int *my_list /* s_list + tid, stride PT; also read by drain(): no restrict */, int &cnt, Body &&body, Drain &&drain) {
     const int a_lo = max(ca - 1, 0), a_hi = min(ca + 1, p.ga - 1);
+    PlaneRows cur, nxt;
+    load_plane_rows(p, cell_start, a_lo, a_hi, cb, cc - 1, cur);
 #pragma unroll 1
     for (int dc = -1; dc <= 1; dc++) {
-        const int c2 = cc + dc;
-        if (c2 < p.c_off || c2 >= p.c_off + p.gcl) continue;
-#pragma unroll 1
-        for (int db = -1; db <= 1; db++) {
-            const int b2 = cb + db;
-            if (b2 < 0 || b2 >= p.gb) continue;
-            const int row = p.ga * (b2 + p.gb * (c2 - p.c_off));
-            int j = __ldg(cell_start + row + a_lo);
-            const int e = __ldg(cell_start + row + a_hi + 1);
+        if (dc < 1) load_plane_rows(p, cell_start, a_lo, a_hi, cb, cc + dc + 1, nxt);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            int j = cur.s[k];
+            const int e = cur.e[k];
             if (cnt + (e - j) <= LIST_K) {
 #pragma unroll 2
                 for (; j < e; j++) {
@@ -69,6 +85,7 @@ __device__ __forceinline__ void sweep_two_phase(const DevParams &p, const int *_
                 }
             }
         }
+        cur = nxt;
     }
     drain();
 }

@@ -1,0 +1,34 @@
+"""GPU x2+: the NCCL slab path (one process per GPU under torchrun) against the single-GPU step — skipped on boxes with fewer
+than two GPUs (the virtual-rank tests in test_gpu_slabs.py cover the same phases on one device)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("extra", [["--canonical"], ["--quadratic", "--dims", "128x20x20"]], ids=["linear-canonical", "quadratic-default"])
+def test_nccl_slabs_match_single_gpu(extra):
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    nproc = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tools", "mg_parity.py"), "--steps", "30"] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["mg_parity"] == "ok" and res["every_particle_owned_once"]
+    if "--canonical" in extra:
+        assert res["max_rel_dev_vs_single_gpu"] <= 2e-6

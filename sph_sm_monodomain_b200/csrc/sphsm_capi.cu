@@ -45,6 +45,10 @@ struct sphsm_handle {
     DevParams dp_uploaded{};
     int n = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t launch_stream = nullptr;  // where LAUNCH enqueues: `stream`, except while the side chain below is built
+    cudaStream_t side_stream = nullptr;    // slab step: moment sums + allreduce + solve run here, beside the sort
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool moments_forked = false;
     Arrays cur{}, alt{};
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
     uint32_t *ghist = nullptr, *tile_state = nullptr, *tile_counter = nullptr;
@@ -102,10 +106,10 @@ struct sphsm_handle {
 static const bool g_sync_debug = getenv("SPHSM_SYNC_DEBUG") != nullptr;
 #define LAUNCH(kern, grid, block, ...)                                                                  \
     do {                                                                                                \
-        kern<<<(grid), (block), 0, h->stream>>>(__VA_ARGS__);                                           \
+        kern<<<(grid), (block), 0, h->launch_stream>>>(__VA_ARGS__);                                    \
         h->launches++;                                                                                  \
         if (g_sync_debug) {                                                                             \
-            cudaError_t e_ = cudaStreamSynchronize(h->stream);                                          \
+            cudaError_t e_ = cudaStreamSynchronize(h->launch_stream);                                   \
             if (e_ != cudaSuccess) {                                                                    \
                 h->err = std::string("kernel ") + #kern + " failed: " + cudaGetErrorString(e_);         \
                 fprintf(stderr, "[sphsm] %s\n", h->err.c_str());                                        \
@@ -291,6 +295,10 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     const int cap = h->alloc_n;
     int rc;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    h->launch_stream = h->stream;
     if ((rc = alloc_arrays(h, h->cur, cap, true)) != 0) return rc;
     if ((rc = alloc_arrays(h, h->alt, cap, false)) != 0) return rc;
     h->alt.COLD_GOAL = h->cur.COLD_GOAL;
@@ -338,6 +346,9 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ev_step0) cudaEventDestroy(h->ev_step0);
     if (h->ev_step1) cudaEventDestroy(h->ev_step1);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SPHSM_OK;
@@ -1326,7 +1337,7 @@ extern "C" int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int c
 // ---- collectives: NCCL (one process per GPU) --------------------------------------------------------------------
 static int comm_allreduce(sphsm_handle *h, int count) {
     if (h->comm_mode != 1 || h->nranks == 1) return SPHSM_OK;  // single GPU; the local group sums between phases
-    NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm, h->stream));
+    NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm, h->launch_stream));
     return SPHSM_OK;
 }
 static int nccl_exchange1(sphsm_handle *h) {
@@ -1393,6 +1404,21 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             h->dp.n = h->n;
             h->mom_n = h->n;
             if (h->gt) h->gt->end_group(KG_OTHER);
+            h->moments_forked = false;
+            if (h->comm_mode == 1 && !h->rest_dirty && !h->profiling) {
+                // the moment sums, their allreduce and the solve only need the unsorted arrays: run them on the side
+                // stream while the main stream hashes and sorts (they rejoin before the gather applies the transform)
+                CU(cudaEventRecord(h->ev_fork, h->stream));
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+                h->launch_stream = h->side_stream;
+                rc = moments_part(h);
+                if (!rc) rc = comm_allreduce(h, h->dp.quadratic ? 33 : 15);
+                if (!rc) LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
+                h->launch_stream = h->stream;
+                if (rc) return rc;
+                CU(cudaEventRecord(h->ev_join, h->side_stream));
+                h->moments_forked = true;
+            }
             if ((rc = grid_sort(h, h->gt)) != 0) return rc;
             LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
             if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
@@ -1421,6 +1447,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             }
             return SPHSM_OK;
         case 3:
+            if (h->moments_forked) return SPHSM_OK;
             if (h->rest_dirty && (rc = rest_part3(h)) != 0) return rc;
             if ((rc = moments_part(h)) != 0) return rc;
             *coll = COLL_ALLREDUCE; *count = h->dp.quadratic ? 33 : 15;
@@ -1430,7 +1457,9 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 h->dp_uploaded = h->dp;
                 CU(cudaMemcpyAsync(h->d_dp, &h->dp_uploaded, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
             }
-            LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
+            if (h->moments_forked) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+            else LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
+            h->moments_forked = false;
             h->mom_n = 0;
             if (h->gt) h->gt->end_group(KG_MOMENTS);
             if (h->n > 0 && (rc = grid_finish(h, h->gt, diag ? 2 : 1, true)) != 0) return rc;

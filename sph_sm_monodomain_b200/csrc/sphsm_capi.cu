@@ -17,6 +17,7 @@
 #include "sphsm_comm.cuh"
 #include "sphsm_pass.cuh"
 #include "sphsm_pass2.cuh"
+#include "sphsm_pass3.cuh"
 #include "sphsm_sm.cuh"
 #include "sphsm_sort.cuh"
 #include "sphsm_types.cuh"
@@ -104,6 +105,9 @@ struct sphsm_handle {
 
 // SPHSM_SYNC_DEBUG=1 in the environment synchronises after every launch and names the kernel that faulted
 static const bool g_sync_debug = getenv("SPHSM_SYNC_DEBUG") != nullptr;
+// SPHSM_PASS=3 selects the experimental warp-staged neighbour passes (sphsm_pass3.cuh; correct, but measured 2x slower than
+// the per-lane gathers of sphsm_pass2.cuh at 8M: profiles/r01_v5_staged_*.json)
+static const int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 2;
 #define LAUNCH(kern, grid, block, ...)                                                                  \
     do {                                                                                                \
         kern<<<(grid), (block), 0, h->launch_stream>>>(__VA_ARGS__);                                    \
@@ -237,6 +241,8 @@ static int alloc_arrays(sphsm_handle *h, Arrays &a, int cap, bool with_cold) {
     CU(cudaMalloc(&a.C, n4)); CU(cudaMalloc(&a.V, n4)); CU(cudaMalloc(&a.S, (size_t)cap * sizeof(float2)));
     CU(cudaMalloc(&a.ACC, n4)); CU(cudaMalloc(&a.GOAL, n4)); CU(cudaMalloc(&a.PV, n4)); CU(cudaMalloc(&a.PB, n4));
     CU(cudaMemset(a.PB, 0, n4));
+    CU(cudaMalloc(&a.VN, (size_t)cap * sizeof(float)));
+    CU(cudaMemset(a.VN, 0, (size_t)cap * sizeof(float)));
     CU(cudaMemset(a.C, 0, n4)); CU(cudaMemset(a.V, 0, n4)); CU(cudaMemset(a.S, 0, (size_t)cap * sizeof(float2)));
     CU(cudaMemset(a.ACC, 0, n4)); CU(cudaMemset(a.GOAL, 0, n4)); CU(cudaMemset(a.PV, 0, n4));
     if (with_cold) {
@@ -247,7 +253,7 @@ static int alloc_arrays(sphsm_handle *h, Arrays &a, int cap, bool with_cold) {
 }
 static void free_arrays(Arrays &a, bool with_cold) {
     cudaFree(a.P); cudaFree(a.VEL); cudaFree(a.O); cudaFree(a.E); cudaFree(a.ID); cudaFree(a.C); cudaFree(a.V);
-    cudaFree(a.S); cudaFree(a.ACC); cudaFree(a.GOAL); cudaFree(a.PV); cudaFree(a.PB);
+    cudaFree(a.S); cudaFree(a.ACC); cudaFree(a.GOAL); cudaFree(a.PV); cudaFree(a.PB); cudaFree(a.VN);
     if (with_cold) { cudaFree(a.COLD_GOAL); cudaFree(a.COLD_PV); }
 }
 
@@ -930,6 +936,23 @@ static int run_stage(sphsm_handle *h, int stage) {
     return SPHSM_OK;
 }
 
+// the fast-path neighbour passes over the owned slot range (count = own_end - own_begin)
+static int launch_pass_a(sphsm_handle *h, int count) {
+    if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+    else LAUNCH(k_pass_a3, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+    return SPHSM_OK;
+}
+static int launch_pass_b(sphsm_handle *h, int count, bool diag) {
+    if (g_pass_gen == 2) {
+        if (diag) LAUNCH(k_pass_b2<true>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b2<false>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+    } else {
+        if (diag) LAUNCH(k_pass_b3<true>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b3<false>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+    }
+    return SPHSM_OK;
+}
+
 // one fused step: grid, shape matching, pass A, pass B
 template <bool STRICT>
 static int fused_step(sphsm_handle *h) {
@@ -958,10 +981,9 @@ static int fused_step(sphsm_handle *h) {
         if (diag) LAUNCH((k_pass_b<STRICT, PB_FUSED_DIAG>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
         else LAUNCH((k_pass_b<STRICT, PB_FUSED>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
     } else {
-        LAUNCH(k_pass_a2, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+        if ((rc = launch_pass_a(h, n)) != 0) return rc;
         gt.end_group(KG_PASS_A);
-        if (diag) LAUNCH(k_pass_b2<true>, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b2<false>, cdiv(n, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);  // single GPU: own range = [0, n)
+        if ((rc = launch_pass_b(h, n, diag)) != 0) return rc;  // single GPU: own range = [0, n)
     }
     std::swap(h->cur.P, h->alt.P);
     gt.end_group(KG_PASS_B);
@@ -1363,12 +1385,16 @@ static int nccl_exchange2(sphsm_handle *h) {
         NC(g_nccl.Send(h->cur.S + ob, (size_t)(h->b2 - ob) * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
         NC(g_nccl.Recv(h->cur.V, (size_t)ob * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
         NC(g_nccl.Recv(h->cur.S, (size_t)ob * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Send(h->cur.VN + ob, (size_t)(h->b2 - ob), NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->cur.VN, (size_t)ob, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
     }
     if (h->rank < h->nranks - 1) {
         NC(g_nccl.Send(h->cur.V + h->b3, (size_t)(oe - h->b3) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
         NC(g_nccl.Send(h->cur.S + h->b3, (size_t)(oe - h->b3) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
         NC(g_nccl.Recv(h->cur.V + oe, (size_t)(n - oe) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
         NC(g_nccl.Recv(h->cur.S + oe, (size_t)(n - oe) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Send(h->cur.VN + h->b3, (size_t)(oe - h->b3), NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->cur.VN + oe, (size_t)(n - oe), NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
     }
     NC(g_nccl.GroupEnd());
     return SPHSM_OK;
@@ -1464,7 +1490,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             if (h->gt) h->gt->end_group(KG_MOMENTS);
             if (h->n > 0 && (rc = grid_finish(h, h->gt, diag ? 2 : 1, true)) != 0) return rc;
             const int nown = h->dp.own_end - h->dp.own_begin;
-            if (nown > 0) LAUNCH(k_pass_a2, cdiv(nown, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+            if (nown > 0 && (rc = launch_pass_a(h, nown)) != 0) return rc;
             if (h->gt) h->gt->end_group(KG_PASS_A);
             *coll = COLL_EXCH2;
             return SPHSM_OK;
@@ -1472,10 +1498,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
         case 5: {  // pass B on the owned slots
             if (h->gt) h->gt->end_group(KG_OTHER);  // exchange 2
             const int nown = h->dp.own_end - h->dp.own_begin;
-            if (nown > 0) {
-                if (diag) LAUNCH(k_pass_b2<true>, cdiv(nown, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
-                else LAUNCH(k_pass_b2<false>, cdiv(nown, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
-            }
+            if (nown > 0 && (rc = launch_pass_b(h, nown, diag)) != 0) return rc;
             std::swap(h->cur.P, h->alt.P);
             if (h->gt) {
                 h->gt->end_group(KG_PASS_B);
@@ -1556,8 +1579,10 @@ extern "C" int sphsm_step_group(sphsm_handle **hs, int nranks, int nsteps) {
                     if (na != nb_halo || nb != na_halo) return fail(a, SPHSM_ERR_COMM, "boundary plane populations differ across a slab face");
                     CU(cudaMemcpy(b->cur.V, a->cur.V + a->b3, (size_t)na * sizeof(float4), cudaMemcpyDeviceToDevice));
                     CU(cudaMemcpy(b->cur.S, a->cur.S + a->b3, (size_t)na * sizeof(float2), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(b->cur.VN, a->cur.VN + a->b3, (size_t)na * sizeof(float), cudaMemcpyDeviceToDevice));
                     CU(cudaMemcpy(a->cur.V + a->dp.own_end, b->cur.V + b->dp.own_begin, (size_t)nb * sizeof(float4), cudaMemcpyDeviceToDevice));
                     CU(cudaMemcpy(a->cur.S + a->dp.own_end, b->cur.S + b->dp.own_begin, (size_t)nb * sizeof(float2), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(a->cur.VN + a->dp.own_end, b->cur.VN + b->dp.own_begin, (size_t)nb * sizeof(float), cudaMemcpyDeviceToDevice));
                 }
             }
         }

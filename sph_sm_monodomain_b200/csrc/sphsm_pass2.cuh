@@ -67,10 +67,21 @@ __device__ __forceinline__ void sweep_two_phase(const DevParams &p, const int *_
             int j = cur.s[k];
             const int e = cur.e[k];
             if (cnt + (e - j) <= LIST_K) {
-#pragma unroll 2
-                for (; j < e; j++) {
-                    if (body(j)) {
+                // candidates two at a time; a row of odd length repeats its last slot with `live` false, so lanes whose
+                // rows differ in parity stay in the same code (the per-row remainder loop was 8 % of the issued
+                // instructions at 19 of 32 lanes, and rows are only 3-6 candidates long on lattice-like inputs)
+#pragma unroll 1
+                for (; j < e; j += 2) {
+                    const bool two = j + 1 < e;
+                    const int j1 = two ? j + 1 : j;
+                    const bool in0 = body(j, true);
+                    const bool in1 = body(j1, two);
+                    if (in0) {
                         my_list[cnt * PT] = j;
+                        cnt++;
+                    }
+                    if (in1) {
+                        my_list[cnt * PT] = j1;
                         cnt++;
                     }
                 }
@@ -78,7 +89,7 @@ __device__ __forceinline__ void sweep_two_phase(const DevParams &p, const int *_
                 if (cnt == LIST_K) drain();  // the unchecked path may have filled the list exactly
 #pragma unroll 1
                 for (; j < e; j++) {
-                    if (body(j)) {
+                    if (body(j, true)) {
                         my_list[cnt * PT] = j;
                         if (++cnt == LIST_K) drain();
                     }
@@ -110,9 +121,9 @@ __global__ void __launch_bounds__(PT) k_pass_a2(const __grid_constant__ DevParam
     if (cell_coords(p, pi.x, pi.y, pi.z, ca, cb, cc)) {
         sweep_two_phase(
             p, cell_start, ca, cb, cc, my_list, cnt,
-            [&](int j) -> bool {
+            [&](int j, bool live) -> bool {
                 const float4 pj = __ldg(P + j);
-                return dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z) <= h2;  // Poly6 support, cpp:151
+                return live && dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z) <= h2;  // Poly6 support, cpp:151
             },
             [&]() {
                 for (int k = 0; k < cnt; k++) {
@@ -137,7 +148,9 @@ __global__ void __launch_bounds__(PT) k_pass_a2(const __grid_constant__ DevParam
     else pres = -0.0f;  // cpp:493-503 (Q2)
     a.VEL[i].w = dens;
     a.S[i] = make_float2(pres, e4.x);
-    a.V[i] = make_float4(fmaf(pvx, p.mix, ci.x), fmaf(pvy, p.mix, ci.y), fmaf(pvz, p.mix, ci.z), __fdiv_rn(pi.w, dens));
+    const float vol = __fdiv_rn(pi.w, dens);  // np->mass / np->dens as pass B reads it, cpp:551
+    a.V[i] = make_float4(fmaf(pvx, p.mix, ci.x), fmaf(pvy, p.mix, ci.y), fmaf(pvz, p.mix, ci.z), vol);
+    a.VN[i] = vol;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -159,6 +172,7 @@ __global__ void __launch_bounds__(PT) k_pass_b2(const __grid_constant__ DevParam
     const float4 *__restrict__ PB = a.PB;
     const float4 *__restrict__ V = a.V;
     const float2 *__restrict__ S = a.S;
+    const float *__restrict__ VN = a.VN;
     const float q2 = g->r2_q2, q1 = g->r2_q1, sp2 = g->r2_spiky;
     const float a1 = g->bs_a1, b1 = g->bs_b1, a2 = g->bs_a2, b2 = g->bs_b2;
     const int z0 = g->zero;
@@ -169,11 +183,11 @@ __global__ void __launch_bounds__(PT) k_pass_b2(const __grid_constant__ DevParam
     if (cell_coords(p, pi.x, pi.y, pi.z, ca, cb, cc)) {
         sweep_two_phase(
             p, cell_start, ca, cb, cc, my_list, cnt,
-            [&](int j) -> bool {
+            [&](int j, bool live) -> bool {
                 const float4 pj = __ldg(PB + j);
-                const float vol = __ldg(&V[j].w);
+                const float vol = __ldg(VN + j);
                 const float r2 = dist2_exact(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                const bool near0 = !(r2 > 1e-12f);        // INF, SPH_SM_monodomain.h:24, cpp:546 (also catches NaN)
+                const bool near0 = !(live && r2 > 1e-12f);  // INF, SPH_SM_monodomain.h:24, cpp:546 (also catches NaN)
                 const bool valid = !near0 && r2 <= q2;    // B_spline_2 support (q < 2), cpp:193
                 const float r2s = valid ? r2 : 1.0f;
                 const float r = r2s * rsqrt_ftz(r2s);

@@ -10,6 +10,7 @@
 //   V    float4  (inter_vel.xyz,     m/dens_new)   written by pass A, gathered by pass B
 //   S    float2  (pres, Vm)                        written by pass A, gathered by pass B
 //   PB   float4  (pos.xyz, Vm)                     written by the reorder, gathered by pass B (fast path)
+//   VN   float   m/dens_new (= V.w), dense         written by pass A, gathered by pass B's phase 1 (fast path)
 //   ACC  float4  (acc.xyz, Inter_Vm)               staged / diagnostics mode only
 //   GOAL float4  (goal.xyz, -)  PV float4 (predicted_vel.xyz, -)   diagnostics mode only
 //   COLD_GOAL / COLD_PV float4 by ORIGINAL index: the frozen mGoalPos / predicted_vel of fixed particles
@@ -59,6 +60,8 @@ struct Arrays {
     float2 *S;
     float4 *ACC, *GOAL, *PV;
     float4 *PB;  // (pos.xyz, Vm): pass B's neighbour record, written by the reorder
+    float *VN;   // m/dens_new again, as a DENSE float array: pass B's phase 1 reads it for every candidate, and a 4-byte
+                 // gather from the 16-byte-strided V.w costs four L1 wavefronts per warp where this costs one
     float4 *COLD_GOAL, *COLD_PV;
 };
 

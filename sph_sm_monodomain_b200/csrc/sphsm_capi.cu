@@ -54,6 +54,8 @@ struct sphsm_handle {
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
     uint32_t *ghist = nullptr, *tile_state = nullptr, *tile_counter = nullptr;
     int sorted_buf = 0;  // which keys[] / vals[] hold the sorted result
+    uint32_t *cell_count = nullptr, *tile_sums = nullptr;  // counting sort: per-cell counts (kept zero between steps), scan scratch
+    bool bounds_ready = false;                             // grid_sort already produced the cell_start table
     int *cell_start = nullptr, *slot_of = nullptr;
     SmState *sm = nullptr;
     double *partial = nullptr, *totals = nullptr;
@@ -262,6 +264,12 @@ static int setup_grid_buffers(sphsm_handle *h) {
     if (h->cell_start) cudaFree(h->cell_start);
     h->cell_start = nullptr;
     CU(cudaMalloc(&h->cell_start, ((size_t)h->dp.num_cells + 2) * sizeof(int)));
+    if (h->cell_count) cudaFree(h->cell_count);
+    if (h->tile_sums) cudaFree(h->tile_sums);
+    h->cell_count = h->tile_sums = nullptr;
+    CU(cudaMalloc(&h->cell_count, ((size_t)h->dp.num_cells + 2 + SCAN_IPT) * sizeof(uint32_t)));
+    CU(cudaMemset(h->cell_count, 0, ((size_t)h->dp.num_cells + 2 + SCAN_IPT) * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->tile_sums, ((size_t)(h->dp.num_cells + 2) / SCAN_TILE + 2) * sizeof(uint32_t)));
     int bits = 1;
     while ((1ll << bits) < (long long)h->dp.num_cells + 1) bits++;
     h->sort_passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
@@ -323,7 +331,7 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaMemset(h->sm, 0, sizeof(SmState)));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, p->device));
-    h->red_blocks = std::max(1, std::min(2 * prop.multiProcessorCount, cdiv(cap, 256)));
+    h->red_blocks = std::max(1, std::min(8 * prop.multiProcessorCount, cdiv(cap, 256)));  // enough loads in flight to cover HBM latency
     CU(cudaMalloc(&h->partial, (size_t)h->red_blocks * 10 * 9 * sizeof(double)));
     CU(cudaMalloc(&h->totals, 128 * sizeof(double)));
     CU(cudaMalloc(&h->scratch, 162 * sizeof(float)));
@@ -342,6 +350,7 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     free_arrays(h->cur, true);
     free_arrays(h->alt, false);
     for (int k = 0; k < 2; k++) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
+    cudaFree(h->cell_count); cudaFree(h->tile_sums);
     cudaFree(h->ghist); cudaFree(h->tile_state); cudaFree(h->tile_counter); cudaFree(h->cell_start); cudaFree(h->slot_of);
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
     cudaFree(h->d_itmp);
@@ -758,8 +767,34 @@ static void swap_sets(sphsm_handle *h, bool all) {
 // permutation), grid_finish() the second (cell table + gather into the new slot order).  The fast path runs the
 // shape-matching sums and solve BETWEEN the two halves (they do not depend on slot order) so that the gather can apply
 // stage 2's per-particle map while the values are in registers (k_reorder_goal).
+static bool use_counting_sort(const sphsm_handle *h) {
+    const int mode = h->prm.reserved[2];  // 0 auto, 1 LSD radix sort, 2 counting sort
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    return (long long)h->dp.num_cells <= 8ll * std::max(h->n, 1) + (1ll << 20);
+}
+
+// one pass over the full key: count per cell -> scan (= the cell table) -> scatter -> canonical in-cell order
+static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt) {
+    const int n = h->n, m = h->dp.num_cells + 1;  // cells + the limbo bucket
+    const int tiles = cdiv(m + 1, SCAN_TILE);
+    LAUNCH(k_cell_count, cdiv(n, 256), 256, h->dp, h->cur.P, h->keys[0], h->keys[1], h->cell_count);
+    if (gt) gt->end_group(KG_HASH);
+    LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
+    LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles);
+    LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start);
+    LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0]);
+    LAUNCH(k_cell_sort_ids, cdiv(h->dp.num_cells, 256), 256, h->cell_start, h->vals[0], h->cur.ID, h->dp.num_cells);
+    h->sorted_buf = 0;
+    h->bounds_ready = true;
+    if (gt) gt->end_group(KG_SORT);
+    return SPHSM_OK;
+}
+
 static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
     const int n = h->n;
+    if (use_counting_sort(h)) return grid_sort_counting(h, gt);
+    h->bounds_ready = false;
     const int passes = h->sort_passes;
     const int tiles = cdiv(n, SORT_TILE);
     CU(cudaMemsetAsync(h->ghist, 0, MAX_SORT_PASSES * RADIX * sizeof(uint32_t), h->stream));
@@ -786,7 +821,7 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
 // fuse_goal: 0 = plain gather; 1 / 2 = gather + goal / predicted / corrected velocity (2 also stores GOAL and PV)
 static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool bounds_done = false) {
     const int n = h->n, src = h->sorted_buf;
-    if (!bounds_done) LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
+    if (!bounds_done && !h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
     if (fuse_goal) {
         if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm);
         else LAUNCH(k_reorder_goal<false>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm);
@@ -1119,23 +1154,23 @@ extern "C" int sphsm_get_cells_csr(sphsm_handle *h, int *cell_start, int *indice
     if (!h->grid_valid && (rc = build_grid(h, nullptr)) != 0) return rc;
     const DevParams &d = h->dp;
     const int n = h->n, ncell = d.g[0] * d.g[1] * d.g[2];
-    std::vector<uint32_t> keys(std::max(n, 1));
+    std::vector<int> cs((size_t)d.num_cells + 2);
     std::vector<int> ids(std::max(n, 1));
-    CU(cudaMemcpyAsync(keys.data(), h->keys[h->sorted_buf], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(cs.data(), h->cell_start, cs.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(ids.data(), h->cur.ID, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     // internal key -> the reference's hash x + Gx*(y + Gy*z) (cpp:142); stable counting sort keeps slot order
-    std::vector<int> ref_hash(n);
+    std::vector<int> ref_hash(n, -1);  // slots of the limbo bucket (outside the grid) stay -1
     std::fill(cell_start, cell_start + ncell + 1, 0);
-    for (int s = 0; s < n; s++) {
-        const uint32_t k = keys[s];
-        if ((int)k >= d.num_cells) { ref_hash[s] = -1; continue; }
+    for (int k = 0; k < d.num_cells; k++) {
+        if (cs[k + 1] == cs[k]) continue;
         int c[3];
-        c[d.perm[0]] = (int)(k % d.ga);
-        c[d.perm[1]] = (int)((k / d.ga) % d.gb);
-        c[d.perm[2]] = (int)(k / ((uint32_t)d.ga * d.gb)) + d.c_off;
-        ref_hash[s] = c[0] + d.g[0] * (c[1] + d.g[1] * c[2]);
-        cell_start[ref_hash[s] + 1]++;
+        c[d.perm[0]] = k % d.ga;
+        c[d.perm[1]] = (k / d.ga) % d.gb;
+        c[d.perm[2]] = k / (d.ga * d.gb) + d.c_off;
+        const int rh = c[0] + d.g[0] * (c[1] + d.g[1] * c[2]);
+        for (int s = cs[k]; s < cs[k + 1]; s++) ref_hash[s] = rh;
+        cell_start[rh + 1] += cs[k + 1] - cs[k];
     }
     for (int c = 0; c < ncell; c++) cell_start[c + 1] += cell_start[c];
     std::vector<int> cursor(cell_start, cell_start + ncell);
@@ -1446,9 +1481,9 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 h->moments_forked = true;
             }
             if ((rc = grid_sort(h, h->gt)) != 0) return rc;
-            LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
+            if (!h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
             if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
-            if (!h->prm.reserved[1] && h->n > 0) {
+            if (!h->bounds_ready && !h->prm.reserved[1] && h->n > 0) {  // (the counting sort leaves every cell in canonical order)
                 // canonical in-cell order (ascending original id) where two ranks must agree slot by slot: the halo
                 // plane and the owned plane on either side of each face (arrivals were appended in atomic order)
                 const int src = h->sorted_buf, ob = h->dp.own_begin, oe = h->dp.own_end;

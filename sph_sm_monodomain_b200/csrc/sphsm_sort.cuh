@@ -243,6 +243,166 @@ __global__ void __launch_bounds__(256) k_cell_bounds(const uint32_t *__restrict_
     }
 }
 
+// ---- one-pass radix (counting) sort with the cell id as the single digit --------------------------------------------------
+// Particles barely move between steps and a cell holds only a few of them, so instead of P LSD passes over 8-bit digits
+// the production path sorts in ONE pass over the full key: count per cell (the atomic's return value is a provisional
+// rank inside the cell), exclusive scan over the cells (which IS the cell_start table the neighbour passes need, so
+// k_cell_bounds disappears), scatter, and a per-cell ordering by original index that makes the result deterministic and
+// equal to the reference's bucket order (push_back order, cpp:207-212).  The LSD radix sort above remains the path for
+// grids with far more cells than particles, where a pass over the cell table would cost more than sorting the keys.
+__global__ void __launch_bounds__(256) k_cell_count(const __grid_constant__ DevParams p, const float4 *__restrict__ P, uint32_t *__restrict__ keys,
+                                                    uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const float4 q = P[i];
+    int ca, cb, cc;
+    const uint32_t key = cell_coords(p, q.x, q.y, q.z, ca, cb, cc) ? (uint32_t)cell_key(p, ca, cb, cc) : (uint32_t)p.num_cells;
+    keys[i] = key;
+    rank[i] = atomicAdd(&cell_count[key], 1u);
+}
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
+
+// sum of each tile of the count table
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t *__restrict__ in, int m, uint32_t *__restrict__ tile_sums) {
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    uint32_t v = 0;
+    if (base + SCAN_IPT <= m) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(in + base), b = *reinterpret_cast<const uint4 *>(in + base + 4);
+        v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    } else {
+        for (int k = 0; k < SCAN_IPT; k++)
+            if (base + k < m) v += in[base + k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; w++) t += s_warp[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+// exclusive scan of the tile sums in place (one block; chunks of 1024 with a running carry)
+__global__ void __launch_bounds__(1024) k_scan_tile_offsets(uint32_t *tile_sums, int nb) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int idx = base + threadIdx.x;
+        const uint32_t v = idx < nb ? tile_sums[idx] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - w;  // exclusive warp bases
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        if (idx < nb) tile_sums[idx] = carry + s_warp[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + inc;
+        __syncthreads();
+    }
+}
+// cell_start[c] = exclusive prefix of the counts for c in [0, m]; the count table is zeroed for the next step
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restrict__ counts, int m, const uint32_t *__restrict__ tile_offsets,
+                                                             int *__restrict__ cell_start) {
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    uint32_t c[SCAN_IPT];
+    const bool full = base + SCAN_IPT <= m;  // 32 contiguous bytes per thread: two 16-byte accesses each way
+    if (full) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(counts + base), b = *reinterpret_cast<const uint4 *>(counts + base + 4);
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) c[k] = base + k < m ? counts[base + k] : 0u;
+    }
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; k++) tsum += c[k];
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++)
+        if (w < warp) wbase += s_warp[w];
+    uint32_t run = tile_offsets[blockIdx.x] + wbase + inc - tsum;
+    if (full) {
+        int o[SCAN_IPT];
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) {
+            o[k] = (int)run;
+            run += c[k];
+        }
+        *reinterpret_cast<int4 *>(cell_start + base) = make_int4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<int4 *>(cell_start + base + 4) = make_int4(o[4], o[5], o[6], o[7]);
+        *reinterpret_cast<uint4 *>(counts + base) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(counts + base + 4) = make_uint4(0u, 0u, 0u, 0u);
+        if (base + SCAN_IPT == m) cell_start[m] = (int)run;  // entry m (= total)
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; k++) {
+            if (base + k <= m) cell_start[base + k] = (int)run;  // entry m (= total) is written by the thread that owns it
+            if (base + k < m) counts[base + k] = 0u;
+            run += c[k];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_cell_scatter(int n, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
+                                                      const int *__restrict__ cell_start, uint32_t *__restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vals[(uint32_t)cell_start[keys[i]] + rank[i]] = (uint32_t)i;
+}
+// in-cell order = ascending ORIGINAL index (one thread per cell; cells hold a handful of particles)
+__global__ void __launch_bounds__(256) k_cell_sort_ids(const int *__restrict__ cell_start, uint32_t *vals, const int *__restrict__ id_src, int num_cells) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= num_cells) return;  // the limbo bucket (outside the grid / dead entries) has no order to keep
+    const int s = cell_start[c], e = cell_start[c + 1];
+    if (e - s < 2) return;
+    if (e - s == 2) {
+        const uint32_t v0 = vals[s], v1 = vals[s + 1];
+        if (id_src[v0] > id_src[v1]) { vals[s] = v1; vals[s + 1] = v0; }
+        return;
+    }
+    for (int i = s + 1; i < e; i++) {
+        const uint32_t v = vals[i];
+        const int vid = id_src[v];
+        int j = i - 1;
+        while (j >= s && id_src[vals[j]] > vid) {
+            vals[j + 1] = vals[j];
+            j--;
+        }
+        vals[j + 1] = v;
+    }
+}
+
 // gather into the new slot order; `all` also permutes the intermediate / diagnostic arrays (after an upload, or
 // in diagnostics mode, they are live across a re-sort)
 __global__ void __launch_bounds__(256) k_reorder(int n, const uint32_t *__restrict__ vals, Arrays src, Arrays dst, int all) {

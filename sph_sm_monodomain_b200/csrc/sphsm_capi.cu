@@ -18,6 +18,7 @@
 #include "sphsm_pass.cuh"
 #include "sphsm_pass2.cuh"
 #include "sphsm_pass3.cuh"
+#include "sphsm_pass4.cuh"
 #include "sphsm_sm.cuh"
 #include "sphsm_sort.cuh"
 #include "sphsm_types.cuh"
@@ -107,9 +108,10 @@ struct sphsm_handle {
 
 // SPHSM_SYNC_DEBUG=1 in the environment synchronises after every launch and names the kernel that faulted
 static const bool g_sync_debug = getenv("SPHSM_SYNC_DEBUG") != nullptr;
-// SPHSM_PASS=3 selects the experimental warp-staged neighbour passes (sphsm_pass3.cuh; correct, but measured 2x slower than
-// the per-lane gathers of sphsm_pass2.cuh at 8M: profiles/r01_v5_staged_*.json)
-static const int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 2;
+// SPHSM_PASS selects the generation of the fast-path neighbour passes: 4 = sphsm_pass4.cuh (production), 2 = sphsm_pass2.cuh
+// (its predecessor), 3 = the experimental warp-staged passes (sphsm_pass3.cuh; correct, but measured 2x slower at 8M:
+// profiles/r01_v5_staged_*.json)
+static const int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 4;
 #define LAUNCH(kern, grid, block, ...)                                                                  \
     do {                                                                                                \
         kern<<<(grid), (block), 0, h->launch_stream>>>(__VA_ARGS__);                                    \
@@ -208,7 +210,7 @@ static void derive_dev_params(sphsm_handle *h) {
     } else {
         d.perm[0] = 0; d.perm[1] = 1; d.perm[2] = 2;
     }
-    d.ga = d.g[d.perm[0]]; d.gb = d.g[d.perm[1]]; d.gc = d.g[d.perm[2]];
+    d.ga = d.g[d.perm[0]] + 2; d.gb = d.g[d.perm[1]] + 2; d.gc = d.g[d.perm[2]];  // ga, gb: one empty border cell per side
     d.c_off = 0; d.gcl = d.gc; d.slab_lo = 0; d.slab_hi = d.gc;
     d.slab_on = 0; d.own_begin = 0; d.own_end = h->n;
     d.num_cells = d.ga * d.gb * d.gcl;
@@ -237,14 +239,14 @@ static void derive_dev_params(sphsm_handle *h) {
 
 // ---------------------------------------------------------------------------------------------------
 static int alloc_arrays(sphsm_handle *h, Arrays &a, int cap, bool with_cold) {
-    size_t n4 = (size_t)cap * sizeof(float4);
+    size_t n4 = ((size_t)cap + 8) * sizeof(float4);  // tail: the pair loops read slot j+1 (masked) up to j+1 == n
     CU(cudaMalloc(&a.P, n4)); CU(cudaMalloc(&a.VEL, n4)); CU(cudaMalloc(&a.O, n4)); CU(cudaMalloc(&a.E, n4));
     CU(cudaMalloc(&a.ID, (size_t)cap * sizeof(int)));
     CU(cudaMalloc(&a.C, n4)); CU(cudaMalloc(&a.V, n4)); CU(cudaMalloc(&a.S, (size_t)cap * sizeof(float2)));
     CU(cudaMalloc(&a.ACC, n4)); CU(cudaMalloc(&a.GOAL, n4)); CU(cudaMalloc(&a.PV, n4)); CU(cudaMalloc(&a.PB, n4));
     CU(cudaMemset(a.PB, 0, n4));
-    CU(cudaMalloc(&a.VN, (size_t)cap * sizeof(float)));
-    CU(cudaMemset(a.VN, 0, (size_t)cap * sizeof(float)));
+    CU(cudaMalloc(&a.VN, ((size_t)cap + 8) * sizeof(float)));
+    CU(cudaMemset(a.VN, 0, ((size_t)cap + 8) * sizeof(float)));
     CU(cudaMemset(a.C, 0, n4)); CU(cudaMemset(a.V, 0, n4)); CU(cudaMemset(a.S, 0, (size_t)cap * sizeof(float2)));
     CU(cudaMemset(a.ACC, 0, n4)); CU(cudaMemset(a.GOAL, 0, n4)); CU(cudaMemset(a.PV, 0, n4));
     if (with_cold) {
@@ -973,12 +975,16 @@ static int run_stage(sphsm_handle *h, int stage) {
 
 // the fast-path neighbour passes over the owned slot range (count = own_end - own_begin)
 static int launch_pass_a(sphsm_handle *h, int count) {
-    if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+    if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+    else if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
     else LAUNCH(k_pass_a3, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
     return SPHSM_OK;
 }
 static int launch_pass_b(sphsm_handle *h, int count, bool diag) {
-    if (g_pass_gen == 2) {
+    if (g_pass_gen == 4) {
+        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b4<false>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+    } else if (g_pass_gen == 2) {
         if (diag) LAUNCH(k_pass_b2<true>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
         else LAUNCH(k_pass_b2<false>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
     } else {
@@ -1165,8 +1171,8 @@ extern "C" int sphsm_get_cells_csr(sphsm_handle *h, int *cell_start, int *indice
     for (int k = 0; k < d.num_cells; k++) {
         if (cs[k + 1] == cs[k]) continue;
         int c[3];
-        c[d.perm[0]] = k % d.ga;
-        c[d.perm[1]] = (k / d.ga) % d.gb;
+        c[d.perm[0]] = k % d.ga - 1;  // (the table has a border cell on either side of these two axes)
+        c[d.perm[1]] = (k / d.ga) % d.gb - 1;
         c[d.perm[2]] = k / (d.ga * d.gb) + d.c_off;
         const int rh = c[0] + d.g[0] * (c[1] + d.g[1] * c[2]);
         for (int s = cs[k]; s < cs[k + 1]; s++) ref_hash[s] = rh;

@@ -25,7 +25,7 @@ struct DevParams {
     int n;
     int g[3];        // Grid_Size (x,y,z), cpp:32-35
     int perm[3];     // key = c[perm0] + G[perm0]*(c[perm1] + G[perm1]*c[perm2]); (0,1,2) = the reference hash
-    int ga, gb, gc;  // G[perm0], G[perm1], G[perm2]
+    int ga, gb, gc;  // G[perm0] + 2, G[perm1] + 2 (one empty border cell on either side, see cell_coords), G[perm2]
     int num_cells;   // ga*gb*gcl; key num_cells is the limbo bucket (outside the grid / NaN)
     float cell_size, h, h2;
     float world[3];
@@ -105,13 +105,15 @@ __device__ __forceinline__ float dist2_exact(float dx, float dy, float dz) {
 
 // Calculate_Cell_Position + the range test of Calculate_Cell_Hash (cpp:127-141): float division by
 // Cell_Size and C truncation.  Returns false for positions outside the grid (or NaN): the limbo bucket.
+// ca and cb are returned BORDER-RELATIVE (+1): the cell table carries one empty cell on either side of the two fast key
+// axes, so the 3x3 rows x 3 cells around any particle exist and the sweeps need neither clamps nor range tests.
 __device__ __forceinline__ bool cell_coords(const DevParams &p, float x, float y, float z, int &ca, int &cb, int &cc) {
     int cx = __float2int_rz(__fdiv_rn(x, p.cell_size));
     int cy = __float2int_rz(__fdiv_rn(y, p.cell_size));
     int cz = __float2int_rz(__fdiv_rn(z, p.cell_size));
     bool ok = (x == x) && (y == y) && (z == z) && cx >= 0 && cx < p.g[0] && cy >= 0 && cy < p.g[1] && cz >= 0 && cz < p.g[2];
-    ca = p.perm[0] == 0 ? cx : (p.perm[0] == 1 ? cy : cz);
-    cb = p.perm[1] == 0 ? cx : (p.perm[1] == 1 ? cy : cz);
+    ca = (p.perm[0] == 0 ? cx : (p.perm[0] == 1 ? cy : cz)) + 1;
+    cb = (p.perm[1] == 0 ? cx : (p.perm[1] == 1 ? cy : cz)) + 1;
     cc = p.perm[2] == 0 ? cx : (p.perm[2] == 1 ? cy : cz);
     if (ok && (cc < p.c_off || cc >= p.c_off + p.gcl)) ok = false;  // outside this rank's slab + halo
     return ok;

@@ -205,7 +205,7 @@ def test_fast_path_equals_diagnostics_path(Sim, name):
         assert bits_equal(pa[f], pb[f]), f
 
 
-@pytest.mark.parametrize("name", ["cfg1_4944", "cube_4913"])
+@pytest.mark.parametrize("name", ["cfg1_4944", "cube_4913", "cfg2_5211_wave"])
 def test_staged_equals_fused(Sim, name):
     """Calling the seven public stage methods one by one (the simple reference-order kernels) equals Animation() (the
     fused two-phase kernels): one step from identical state within TOL; three steps with the amplified classes."""

@@ -179,9 +179,21 @@ __global__ void __launch_bounds__(PT) k_pass_a4(const __grid_constant__ DevParam
 
 // ---------------------------------------------------------------------------------------------------
 // Update_Properties (cpp:602-649) with reciprocals on the velocity / position side.  The voltage side of the step (ionic
-// model, Inter_Vm, the Vm update) keeps the reference's exact operations: the excitable dynamics amplify a last-bit
-// difference in Vm a thousandfold within 50 steps (a float ionic model + reciprocal mass put the cfg2 wave 0.11 away
-// from the reference at step 50, ten times the reference's own -O2 / -Ofast spread), and it is O(1) work per particle.
+// model with its double promotions, Inter_Vm, the Vm update) keeps the reference's exact operations by default: Vm then
+// stays BIT-IDENTICAL to the reference wherever the Laplacian vanishes (both Resources/*.csv configs as main.cpp runs
+// them), and the excitable dynamics amplify rounding differences (cfg2 wave, |dVm| max at step 200: 2.8e-2 exact,
+// 6.7e-2 with -DSPHSM_FAST_ODE=1, for 22 us of 717 at 8M).
+#ifndef SPHSM_FAST_ODE
+#define SPHSM_FAST_ODE 0
+#endif
+__device__ __forceinline__ void cell_model_fast(const DevParams &p, float Vm, float inv_mass, float &Iion, float &w) {
+    const float u = (Vm - p.Vr) / p.fh_denom;
+    const float c1 = p.C1 * u * (u - p.fh_asd);
+    const float t = fmaf(c1, u - 1.0f, p.C2 * w);
+    const float dtm = p.dt * inv_mass;
+    Iion = fmaf(dtm, t, Iion);
+    w = fmaf(dtm * p.C3, u - p.C4 * w, w);
+}
 __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, float dtm, float ivx, float ivy, float ivz, float ax, float ay, float az,
                                                float inter_vm, float mass, float &x, float &y, float &z, float &vx, float &vy, float &vz, float &Vm) {
     if (!fixed) {
@@ -192,7 +204,7 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
         y = fmaf(vy, p.dt, y);
         z = fmaf(vz, p.dt, z);
     }
-    Vm = Vm + (inter_vm * p.dt) / mass;  // cpp:612
+    Vm = SPHSM_FAST_ODE ? fmaf(inter_vm, dtm, Vm) : Vm + (inter_vm * p.dt) / mass;  // cpp:612
     Vm = fminf(fmaxf(Vm, -p.max_voltage), p.max_voltage);
     // walls (cpp:620-646); the final bounds.clamp (m3Bounds.h:84-88) cannot move a position that passed them
     if (x < 0.0f) { vx *= p.wall_hit; x = 0.0f; }
@@ -217,7 +229,8 @@ __global__ void __launch_bounds__(PT) k_pass_b4(const __grid_constant__ DevParam
     const float pres_i = a.S[i].x;
     const float Vm_i = e4.x;
     const float inv_mass = rcp_ftz(pi.w);
-    cell_model<false>(p, e4.x, pi.w, e4.y, e4.z);
+    if (SPHSM_FAST_ODE) cell_model_fast(p, e4.x, inv_mass, e4.y, e4.z);
+    else cell_model<false>(p, e4.x, pi.w, e4.y, e4.z);
 
     const int z0 = g->zero;  // == 0, loaded from global: what is derived from it stays in registers (see list_put)
     const float4 *__restrict__ PB = pinned(a.PB, z0);
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(PT) k_pass_b4(const __grid_constant__ DevParam
     az *= inv_dens;
     // cpp:571: Inter_Vm += (sigma/(Beta*Cm))*Inter_Vm - ((Iion - stim*dt/mass)/Cm)   (the += form, Q9)
     const float dtm = p.dt * inv_mass;
-    const float ivm = L + (p.diff_coef * L - (e4.y - (e4.w * p.dt) / pi.w) / p.Cm);
+    const float ivm = SPHSM_FAST_ODE ? L + (p.diff_coef * L - (e4.y - e4.w * dtm) / p.Cm) : L + (p.diff_coef * L - (e4.y - (e4.w * p.dt) / pi.w) / p.Cm);
     if (DIAG) a.ACC[i] = make_float4(ax, ay, az, ivm);
     const bool fixed = __float_as_int(a.O[i].w) != 0;
     float x = pi.x, y = pi.y, z = pi.z;

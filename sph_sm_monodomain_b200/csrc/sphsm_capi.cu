@@ -1008,8 +1008,21 @@ static int fused_step(sphsm_handle *h) {
     GroupTimer gt(h);
     if (!STRICT && n > 1) {
         // sort -> shape-matching transform (slot-order independent) -> cell table + gather fused with stage 2's map
+        // the moment sums and the solve only read the not-yet-sorted arrays: they run on the side stream beside the sort
+        // and rejoin before the gather applies the transform (kept in line while the per-group timers are on)
+        const bool fork = !h->rest_dirty && !h->profiling;
+        if (fork) {
+            CU(cudaEventRecord(h->ev_fork, h->stream));
+            CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            h->launch_stream = h->side_stream;
+            rc = sm_transform_fast(h);
+            h->launch_stream = h->stream;
+            if (rc) return rc;
+            CU(cudaEventRecord(h->ev_join, h->side_stream));
+        }
         if ((rc = grid_sort(h, &gt)) != 0) return rc;
-        if ((rc = sm_transform_fast(h)) != 0) return rc;
+        if (fork) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        else if ((rc = sm_transform_fast(h)) != 0) return rc;
         gt.end_group(KG_MOMENTS);
         if ((rc = grid_finish(h, &gt, diag ? 2 : 1)) != 0) return rc;
     } else {

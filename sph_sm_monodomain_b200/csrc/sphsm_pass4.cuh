@@ -109,7 +109,7 @@ __device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict
 
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
-__global__ void __launch_bounds__(PT) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+__global__ void __launch_bounds__(PT, 10) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 const int *__restrict__ cell_start) {
     __shared__ int s_list[LIST_K * PT];
     const int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
@@ -218,7 +218,7 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
 // pass B: ionic cell model + pressure / viscosity force + SPH Laplacian of Vm + integration and walls
 // (reference cpp:575-593, 515-573, 598-651).  PB = (pos.xyz, Vm) is the neighbour record of this pass.
 template <bool DIAG>
-__global__ void __launch_bounds__(PT) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+__global__ void __launch_bounds__(PT, 8) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 float4 *__restrict__ Pout, const int *__restrict__ cell_start) {
     __shared__ int s_list[LIST_K * PT];
     const int i = p.own_begin + blockIdx.x * PT + threadIdx.x;

@@ -887,7 +887,9 @@ static int rest_part3(sphsm_handle *h) {
     return SPHSM_OK;
 }
 static int moments_part(sphsm_handle *h) {
-    const int B = h->red_blocks;
+    // one partial per block and a 33-double block reduction each: keep >= 2048 particles per block (at a slab's 1M
+    // particles the full 8 x SMs grid spent most of its 32 us in the reductions)
+    const int B = std::max(1, std::min(h->red_blocks, cdiv(std::max(moment_params(h).n, 1), 2048)));
     if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, moment_params(h), h->cur.P, h->cur.O, h->sm, h->partial);
     else LAUNCH(k_moments<3>, B, 256, moment_params(h), h->cur.P, h->cur.O, h->sm, h->partial);
     const int nacc = h->dp.quadratic ? 33 : 15;

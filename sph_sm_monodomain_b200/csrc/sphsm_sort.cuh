@@ -253,12 +253,30 @@ __global__ void __launch_bounds__(256) k_cell_bounds(const uint32_t *__restrict_
 __global__ void __launch_bounds__(256) k_cell_count(const __grid_constant__ DevParams p, const float4 *__restrict__ P, uint32_t *__restrict__ keys,
                                                     uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n) return;
-    const float4 q = P[i];
-    int ca, cb, cc;
-    const uint32_t key = cell_coords(p, q.x, q.y, q.z, ca, cb, cc) ? (uint32_t)cell_key(p, ca, cb, cc) : (uint32_t)p.num_cells;
-    keys[i] = key;
-    rank[i] = atomicAdd(&cell_count[key], 1u);
+    const bool live = i < p.n;
+    uint32_t key = (uint32_t)p.num_cells;
+    if (live) {
+        const float4 q = P[i];
+        int ca, cb, cc;
+        if (cell_coords(p, q.x, q.y, q.z, ca, cb, cc)) key = (uint32_t)cell_key(p, ca, cb, cc);
+    }
+    // The limbo bucket (outside the grid; in slab mode every dead slot of the two message regions, tens of thousands of
+    // CONSECUTIVE entries) is counted once per warp: one atomic per entry on that single address serialised the whole
+    // kernel (78 us at 1M + 88k dead entries, against 52 us for 8M entries without them).
+    const bool limbo = live && key == (uint32_t)p.num_cells;
+    const unsigned lm = __ballot_sync(0xffffffffu, limbo);
+    uint32_t r = 0;
+    if (limbo) {
+        const int lane = threadIdx.x & 31, leader = __ffs(lm) - 1;
+        if (lane == leader) r = atomicAdd(&cell_count[key], (uint32_t)__popc(lm));
+        r = __shfl_sync(lm, r, leader) + (uint32_t)__popc(lm & ((1u << lane) - 1u));
+    } else if (live) {
+        r = atomicAdd(&cell_count[key], 1u);
+    }
+    if (live) {
+        keys[i] = key;
+        rank[i] = r;
+    }
 }
 
 constexpr int SCAN_THREADS = 256;

@@ -91,7 +91,8 @@ struct sphsm_handle {
     int *d_err = nullptr, *d_meta = nullptr, *h_meta = nullptr;
     int b2 = 0, b3 = 0;       // start of the 2nd / of the last owned plane (exchange-2 ranges)
     int n_global = 0;         // particles uploaded before sphsm_comm_set_slab filtered them (ids are global)
-    int mom_n = 0;            // slab step: extent of the PRE-reorder arrays (old slots + both message regions) the moment sums scan
+    int mom_n = 0;            // slab step: extent of the PRE-reorder arrays (old slots + both message regions) the REST-state sums scan
+    int mom_begin = 0, mom_end = 0;  // slab step: the slots this rank integrated last step; its share of the per-step moment sums
     struct GroupTimer *gt = nullptr;
 };
 
@@ -889,9 +890,19 @@ static int rest_part3(sphsm_handle *h) {
 static int moments_part(sphsm_handle *h) {
     // one partial per block and a 33-double block reduction each: keep >= 2048 particles per block (at a slab's 1M
     // particles the full 8 x SMs grid spent most of its 32 us in the reductions)
-    const int B = std::max(1, std::min(h->red_blocks, cdiv(std::max(moment_params(h).n, 1), 2048)));
-    if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, moment_params(h), h->cur.P, h->cur.O, h->sm, h->partial);
-    else LAUNCH(k_moments<3>, B, 256, moment_params(h), h->cur.P, h->cur.O, h->sm, h->partial);
+    // Slab mode: every particle is summed by the rank that integrated it last step, i.e. over that rank's owned slot range
+    // as it stood BEFORE this step's exchange (migrants on their way out included, arrivals not): each particle exactly
+    // once across ranks, and the sums need neither the exchange nor the sort, so they start with the step.
+    DevParams d = h->dp;
+    int off = 0;
+    if (d.slab_on) {
+        off = h->mom_begin;
+        d.n = h->mom_end - h->mom_begin;
+        d.slab_on = 0;
+    }
+    const int B = std::max(1, std::min(h->red_blocks, cdiv(std::max(d.n, 1), 2048)));
+    if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, d, h->cur.P + off, h->cur.O + off, h->sm, h->partial);
+    else LAUNCH(k_moments<3>, B, 256, d, h->cur.P + off, h->cur.O + off, h->sm, h->partial);
     const int nacc = h->dp.quadratic ? 33 : 15;
     LAUNCH(k_sum_partials_par, nacc, 256, h->partial, B, nacc, h->totals);
     return SPHSM_OK;
@@ -1468,6 +1479,22 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
     switch (phase) {
         case 0: {  // classify + pack
             if (h->profiling) h->gt = new GroupTimer(h);
+            h->mom_begin = h->dp.own_begin;
+            h->mom_end = h->dp.own_end;
+            h->moments_forked = false;
+            if (h->comm_mode == 1 && !h->rest_dirty && !h->profiling) {
+                // the moment sums, their allreduce and the solve only need last step's owned slots: they run on the side
+                // stream beside the exchange, the hash and the sort, and rejoin before the gather applies the transform
+                CU(cudaEventRecord(h->ev_fork, h->stream));
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+                h->launch_stream = h->side_stream;
+                // (NCCL runs one communicator's operations in issue order whatever their streams: the allreduce is issued
+                // after exchange 1, in mg_forked_allreduce, so that the exchange does not queue behind the sums)
+                rc = moments_part(h);
+                h->launch_stream = h->stream;
+                if (rc) return rc;
+                h->moments_forked = true;
+            }
             CU(cudaMemsetAsync(h->msg_send[0], 0, 16, h->stream));
             CU(cudaMemsetAsync(h->msg_send[1], 0, 16, h->stream));
             if (h->n > 0)
@@ -1486,21 +1513,6 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             h->dp.n = h->n;
             h->mom_n = h->n;
             if (h->gt) h->gt->end_group(KG_OTHER);
-            h->moments_forked = false;
-            if (h->comm_mode == 1 && !h->rest_dirty && !h->profiling) {
-                // the moment sums, their allreduce and the solve only need the unsorted arrays: run them on the side
-                // stream while the main stream hashes and sorts (they rejoin before the gather applies the transform)
-                CU(cudaEventRecord(h->ev_fork, h->stream));
-                CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-                h->launch_stream = h->side_stream;
-                rc = moments_part(h);
-                if (!rc) rc = comm_allreduce(h, h->dp.quadratic ? 33 : 15);
-                if (!rc) LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
-                h->launch_stream = h->stream;
-                if (rc) return rc;
-                CU(cudaEventRecord(h->ev_join, h->side_stream));
-                h->moments_forked = true;
-            }
             if ((rc = grid_sort(h, h->gt)) != 0) return rc;
             if (!h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
             if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
@@ -1579,12 +1591,26 @@ static int mg_check(sphsm_handle *h) {
     return SPHSM_OK;
 }
 
+// second half of the forked moment chain: allreduce + solve on the side stream, then the join event
+static int mg_forked_allreduce(sphsm_handle *h) {
+    h->launch_stream = h->side_stream;
+    int rc = comm_allreduce(h, h->dp.quadratic ? 33 : 15);
+    if (!rc) rc = [&]() -> int { LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm); return SPHSM_OK; }();
+    h->launch_stream = h->stream;
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev_join, h->side_stream));
+    return SPHSM_OK;
+}
+
 static int mg_step_nccl(sphsm_handle *h) {
     int rc, coll, count;
     if ((rc = mg_check(h)) != 0) return rc;
     for (int ph = 0; ph < MG_PHASES; ph++) {
         if ((rc = mg_phase(h, ph, &coll, &count)) != 0) return rc;
-        if (coll == COLL_EXCH1) rc = nccl_exchange1(h);
+        if (coll == COLL_EXCH1) {
+            rc = nccl_exchange1(h);
+            if (!rc && h->moments_forked) rc = mg_forked_allreduce(h);
+        }
         else if (coll == COLL_ALLREDUCE) rc = comm_allreduce(h, count);
         else if (coll == COLL_EXCH2) rc = nccl_exchange2(h);
         if (rc) return rc;

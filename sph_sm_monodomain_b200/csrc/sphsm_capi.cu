@@ -49,8 +49,10 @@ struct sphsm_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t launch_stream = nullptr;  // where LAUNCH enqueues: `stream`, except while the side chain below is built
     cudaStream_t side_stream = nullptr;    // slab step: moment sums + allreduce + solve run here, beside the sort
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_meta = nullptr, ev_bnd = nullptr, ev_int = nullptr;
     bool moments_forked = false;
+    bool reordered = false;                // slab step: the gather was queued before the plane boundaries reached the host
+    bool split = false;                    // slab step: exchange 2 in flight on the side stream beside the interior planes
     Arrays cur{}, alt{};
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
     uint32_t *ghist = nullptr, *tile_state = nullptr, *tile_counter = nullptr;
@@ -213,7 +215,7 @@ static void derive_dev_params(sphsm_handle *h) {
     }
     d.ga = d.g[d.perm[0]] + 2; d.gb = d.g[d.perm[1]] + 2; d.gc = d.g[d.perm[2]];  // ga, gb: one empty border cell per side
     d.c_off = 0; d.gcl = d.gc; d.slab_lo = 0; d.slab_hi = d.gc;
-    d.slab_on = 0; d.own_begin = 0; d.own_end = h->n;
+    d.slab_on = 0; d.own_begin = 0; d.own_end = h->n; d.hole_begin = 0; d.hole_len = 0;
     d.num_cells = d.ga * d.gb * d.gcl;
     d.K = q.K; d.rho0 = q.stand_density; d.dt = q.time_delta; d.inv_dt = 1.0f / q.time_delta;  // cpp:661
     d.wall_hit = q.wall_hit; d.mu = q.mu; d.mix = q.velocity_mixing;
@@ -312,9 +314,16 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     const int cap = h->alloc_n;
     int rc;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    {
+        int prio_lo = 0, prio_hi = 0;  // the side stream carries the short chains everything else waits for
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi));
+    }
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_meta, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming));
     h->launch_stream = h->stream;
     if ((rc = alloc_arrays(h, h->cur, cap, true)) != 0) return rc;
     if ((rc = alloc_arrays(h, h->alt, cap, false)) != 0) return rc;
@@ -366,6 +375,9 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     if (h->ev_step1) cudaEventDestroy(h->ev_step1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_meta) cudaEventDestroy(h->ev_meta);
+    if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
+    if (h->ev_int) cudaEventDestroy(h->ev_int);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -822,12 +834,13 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
 }
 
 // fuse_goal: 0 = plain gather; 1 / 2 = gather + goal / predicted / corrected velocity (2 also stores GOAL and PV)
-static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool bounds_done = false) {
+// n_dev != nullptr: the live count is read from device memory (grid sized for h->n, an upper bound)
+static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool bounds_done = false, const int *n_dev = nullptr) {
     const int n = h->n, src = h->sorted_buf;
     if (!bounds_done && !h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
     if (fuse_goal) {
-        if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm);
-        else LAUNCH(k_reorder_goal<false>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm);
+        if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev);
+        else LAUNCH(k_reorder_goal<false>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev);
         swap_sets(h, false);
         std::swap(h->cur.C, h->alt.C);
         std::swap(h->cur.GOAL, h->alt.GOAL);
@@ -987,22 +1000,31 @@ static int run_stage(sphsm_handle *h, int stage) {
 }
 
 // the fast-path neighbour passes over the owned slot range (count = own_end - own_begin)
-static int launch_pass_a(sphsm_handle *h, int count) {
-    if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
-    else if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
-    else LAUNCH(k_pass_a3, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->cell_start);
+// slots [begin, end) minus the hole [hole_b, hole_e) (generation-4 kernels only)
+static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0) {
+    const int count = end - begin - (hole_e - hole_b);
+    if (count <= 0) return SPHSM_OK;
+    DevParams d = h->dp;
+    d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
+    if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
+    else if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
+    else LAUNCH(k_pass_a3, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
     return SPHSM_OK;
 }
-static int launch_pass_b(sphsm_handle *h, int count, bool diag) {
+static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hole_b = 0, int hole_e = 0) {
+    const int count = end - begin - (hole_e - hole_b);
+    if (count <= 0) return SPHSM_OK;
+    DevParams d = h->dp;
+    d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
     if (g_pass_gen == 4) {
-        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b4<false>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b4<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
     } else if (g_pass_gen == 2) {
-        if (diag) LAUNCH(k_pass_b2<true>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b2<false>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        if (diag) LAUNCH(k_pass_b2<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b2<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
     } else {
-        if (diag) LAUNCH(k_pass_b3<true>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b3<false>, cdiv(count, PT), PT, h->dp, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        if (diag) LAUNCH(k_pass_b3<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b3<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
     }
     return SPHSM_OK;
 }
@@ -1048,9 +1070,9 @@ static int fused_step(sphsm_handle *h) {
         if (diag) LAUNCH((k_pass_b<STRICT, PB_FUSED_DIAG>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
         else LAUNCH((k_pass_b<STRICT, PB_FUSED>), cdiv(n, 128), 128, h->dp, h->cur, h->alt.P, h->cell_start);
     } else {
-        if ((rc = launch_pass_a(h, n)) != 0) return rc;
+        if ((rc = launch_pass_a(h, 0, n)) != 0) return rc;  // single GPU: own range = [0, n)
         gt.end_group(KG_PASS_A);
-        if ((rc = launch_pass_b(h, n, diag)) != 0) return rc;  // single GPU: own range = [0, n)
+        if ((rc = launch_pass_b(h, 0, n, diag)) != 0) return rc;
     }
     std::swap(h->cur.P, h->alt.P);
     gt.end_group(KG_PASS_B);
@@ -1356,11 +1378,15 @@ extern "C" int sphsm_comm_init_local(sphsm_handle **hs, int nranks) {
 }
 
 // read the plane boundaries back (one 32-byte copy + stream sync) and set n / owned range from them
-static int slab_meta(sphsm_handle *h) {
+static int slab_meta_launch(sphsm_handle *h) {
     const DevParams &d = h->dp;
     LAUNCH(k_mg_meta, 1, 32, h->cell_start, d.num_cells, d.ga * d.gb, d.gcl, h->d_err, h->d_meta);
     CU(cudaMemcpyAsync(h->h_meta, h->d_meta, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventRecord(h->ev_meta, h->stream));
+    return SPHSM_OK;
+}
+static int slab_meta_read(sphsm_handle *h) {
+    CU(cudaEventSynchronize(h->ev_meta));  // (not the stream: work queued behind the read-back keeps running)
     const int *m = h->h_meta;
     if (m[5]) return fail(h, SPHSM_ERR_COMM, "a particle crossed more than one cell plane in one step (or left the slab window)");
     if (m[6]) return fail(h, SPHSM_ERR_COMM, "halo message overflow: raise params.reserved[0] (halo capacity)");
@@ -1371,6 +1397,10 @@ static int slab_meta(sphsm_handle *h) {
     h->b3 = m[3];
     h->dp.own_end = m[4];
     return SPHSM_OK;
+}
+static int slab_meta(sphsm_handle *h) {
+    int rc = slab_meta_launch(h);
+    return rc ? rc : slab_meta_read(h);
 }
 
 extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
@@ -1444,24 +1474,24 @@ static int nccl_exchange1(sphsm_handle *h) {
     return SPHSM_OK;
 }
 // boundary planes' pass-A results: V = (inter_vel, m/dens) and S = (pres, Vm), contiguous slot ranges on both sides
-static int nccl_exchange2(sphsm_handle *h) {
+static int nccl_exchange2(sphsm_handle *h, cudaStream_t st) {
     const int ob = h->dp.own_begin, oe = h->dp.own_end, n = h->n;
     NC(g_nccl.GroupStart());
     if (h->rank > 0) {
-        NC(g_nccl.Send(h->cur.V + ob, (size_t)(h->b2 - ob) * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Send(h->cur.S + ob, (size_t)(h->b2 - ob) * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(h->cur.V, (size_t)ob * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(h->cur.S, (size_t)ob * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Send(h->cur.VN + ob, (size_t)(h->b2 - ob), NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(h->cur.VN, (size_t)ob, NCCL_FLOAT, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Send(h->cur.V + ob, (size_t)(h->b2 - ob) * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->cur.S + ob, (size_t)(h->b2 - ob) * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.V, (size_t)ob * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.S, (size_t)ob * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->cur.VN + ob, (size_t)(h->b2 - ob), NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.VN, (size_t)ob, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
     }
     if (h->rank < h->nranks - 1) {
-        NC(g_nccl.Send(h->cur.V + h->b3, (size_t)(oe - h->b3) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Send(h->cur.S + h->b3, (size_t)(oe - h->b3) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(h->cur.V + oe, (size_t)(n - oe) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(h->cur.S + oe, (size_t)(n - oe) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Send(h->cur.VN + h->b3, (size_t)(oe - h->b3), NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(h->cur.VN + oe, (size_t)(n - oe), NCCL_FLOAT, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Send(h->cur.V + h->b3, (size_t)(oe - h->b3) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->cur.S + h->b3, (size_t)(oe - h->b3) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.V + oe, (size_t)(n - oe) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.S + oe, (size_t)(n - oe) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->cur.VN + h->b3, (size_t)(oe - h->b3), NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.VN + oe, (size_t)(n - oe), NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
     }
     NC(g_nccl.GroupEnd());
     return SPHSM_OK;
@@ -1515,7 +1545,17 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             if (h->gt) h->gt->end_group(KG_OTHER);
             if ((rc = grid_sort(h, h->gt)) != 0) return rc;
             if (!h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
-            if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
+            h->reordered = false;
+            if (h->moments_forked && h->bounds_ready) {
+                // the gather needs the live count only as a bound: it is queued behind the read-back with the count taken
+                // from device memory, so the GPU is busy while the host waits for the plane boundaries
+                if ((rc = slab_meta_launch(h)) != 0) return rc;
+                CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+                h->moments_forked = false;
+                if ((rc = grid_finish(h, h->gt, diag ? 2 : 1, true, h->d_meta)) != 0) return rc;
+                h->reordered = true;
+                if ((rc = slab_meta_read(h)) != 0) return rc;
+            } else if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
             if (!h->bounds_ready && !h->prm.reserved[1] && h->n > 0) {  // (the counting sort leaves every cell in canonical order)
                 // canonical in-cell order (ascending original id) where two ranks must agree slot by slot: the halo
                 // plane and the owned plane on either side of each face (arrivals were appended in atomic order)
@@ -1541,7 +1581,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             }
             return SPHSM_OK;
         case 3:
-            if (h->moments_forked) return SPHSM_OK;
+            if (h->moments_forked || h->reordered) return SPHSM_OK;
             if (h->rest_dirty && (rc = rest_part3(h)) != 0) return rc;
             if ((rc = moments_part(h)) != 0) return rc;
             *coll = COLL_ALLREDUCE; *count = h->dp.quadratic ? 33 : 15;
@@ -1551,22 +1591,52 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 h->dp_uploaded = h->dp;
                 CU(cudaMemcpyAsync(h->d_dp, &h->dp_uploaded, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
             }
-            if (h->moments_forked) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+            if (h->reordered) {
+            } else if (h->moments_forked) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
             else LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
             h->moments_forked = false;
             h->mom_n = 0;
             if (h->gt) h->gt->end_group(KG_MOMENTS);
-            if (h->n > 0 && (rc = grid_finish(h, h->gt, diag ? 2 : 1, true)) != 0) return rc;
-            const int nown = h->dp.own_end - h->dp.own_begin;
-            if (nown > 0 && (rc = launch_pass_a(h, nown)) != 0) return rc;
+            if (h->n > 0 && !h->reordered && (rc = grid_finish(h, h->gt, diag ? 2 : 1, true)) != 0) return rc;
+            const int ob = h->dp.own_begin, oe = h->dp.own_end;
+            // NCCL mode with at least three owned planes: pass A on the two boundary planes first, their V / S records travel
+            // on the side stream while the interior planes are computed here (and pass B's interior after them)
+            h->split = h->comm_mode == 1 && h->nranks > 1 && !h->profiling && h->b2 < h->b3 && g_pass_gen == 4;
+            if (h->split) {
+                // side stream (high priority): pass A on the two boundary planes -> exchange 2 -> pass B on them;
+                // main stream: pass A, then pass B on the interior planes.  Cross dependencies: pass B's interior reads the
+                // boundary planes' pass-A records (ev_bnd), pass B's boundary reads the interior's (ev_int).
+                CU(cudaEventRecord(h->ev_fork, h->stream));
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+                h->launch_stream = h->side_stream;
+                rc = launch_pass_a(h, ob, oe, h->b2, h->b3);
+                h->launch_stream = h->stream;
+                if (rc) return rc;
+                CU(cudaEventRecord(h->ev_bnd, h->side_stream));
+                if ((rc = nccl_exchange2(h, h->side_stream)) != 0) return rc;
+                if ((rc = launch_pass_a(h, h->b2, h->b3)) != 0) return rc;
+                CU(cudaEventRecord(h->ev_int, h->stream));
+                return SPHSM_OK;
+            }
+            if ((rc = launch_pass_a(h, ob, oe)) != 0) return rc;
             if (h->gt) h->gt->end_group(KG_PASS_A);
             *coll = COLL_EXCH2;
             return SPHSM_OK;
         }
         case 5: {  // pass B on the owned slots
             if (h->gt) h->gt->end_group(KG_OTHER);  // exchange 2
-            const int nown = h->dp.own_end - h->dp.own_begin;
-            if (nown > 0 && (rc = launch_pass_b(h, nown, diag)) != 0) return rc;
+            const int ob = h->dp.own_begin, oe = h->dp.own_end;
+            if (h->split) {  // interior planes need no halo record; the boundary planes wait for exchange 2 (stream order)
+                CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
+                if ((rc = launch_pass_b(h, h->b2, h->b3, diag)) != 0) return rc;
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_int, 0));
+                h->launch_stream = h->side_stream;
+                rc = launch_pass_b(h, ob, oe, diag, h->b2, h->b3);
+                h->launch_stream = h->stream;
+                if (rc) return rc;
+                CU(cudaEventRecord(h->ev_join, h->side_stream));
+                CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+            } else if ((rc = launch_pass_b(h, ob, oe, diag)) != 0) return rc;
             std::swap(h->cur.P, h->alt.P);
             if (h->gt) {
                 h->gt->end_group(KG_PASS_B);
@@ -1612,7 +1682,7 @@ static int mg_step_nccl(sphsm_handle *h) {
             if (!rc && h->moments_forked) rc = mg_forked_allreduce(h);
         }
         else if (coll == COLL_ALLREDUCE) rc = comm_allreduce(h, count);
-        else if (coll == COLL_EXCH2) rc = nccl_exchange2(h);
+        else if (coll == COLL_EXCH2) rc = nccl_exchange2(h, h->stream);
         if (rc) return rc;
     }
     return SPHSM_OK;

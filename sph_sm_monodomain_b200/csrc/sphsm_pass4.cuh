@@ -112,7 +112,8 @@ __device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict
 __global__ void __launch_bounds__(PT, 10) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 const int *__restrict__ cell_start) {
     __shared__ int s_list[LIST_K * PT];
-    const int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
+    int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
+    if (i >= p.hole_begin) i += p.hole_len;
     if (i >= p.own_end) return;
     const float4 pi = a.P[i];
     const float4 ci = a.C[i];
@@ -221,7 +222,8 @@ template <bool DIAG>
 __global__ void __launch_bounds__(PT, 8) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 float4 *__restrict__ Pout, const int *__restrict__ cell_start) {
     __shared__ int s_list[LIST_K * PT];
-    const int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
+    int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
+    if (i >= p.hole_begin) i += p.hole_len;
     if (i >= p.own_end) return;
     const float4 pi = a.P[i];
     const float4 vi = a.V[i];

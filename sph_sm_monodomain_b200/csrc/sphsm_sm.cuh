@@ -474,9 +474,9 @@ __global__ void __launch_bounds__(256) k_goal_cvel(const __grid_constant__ DevPa
 // step from pass B's moment partials).  Saves the separate 48 B/particle re-read of k_goal_cvel.
 template <bool DIAG>
 __global__ void __launch_bounds__(256) k_reorder_goal(const __grid_constant__ DevParams p, const uint32_t *__restrict__ vals, Arrays src,
-                                                      Arrays dst, const SmState *__restrict__ sm) {
+                                                      Arrays dst, const SmState *__restrict__ sm, const int *__restrict__ n_dev) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n) return;
+    if (s >= (n_dev ? *n_dev : p.n)) return;  // n_dev: the live count is still on its way to the host (slab step)
     const uint32_t v = vals[s];
     const float4 p4 = src.P[v], v4 = src.VEL[v], o4 = src.O[v], e4 = src.E[v];
     dst.P[s] = p4;

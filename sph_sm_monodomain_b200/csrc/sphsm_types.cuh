@@ -50,6 +50,7 @@ struct DevParams {
     int c_off, gcl, slab_lo, slab_hi;
     int slab_on;              // 1: multi-GPU slab mode (sums and outputs cover owned particles only)
     int own_begin, own_end;   // slot range the neighbour passes compute ([0, n) on a single GPU)
+    int hole_begin, hole_len; // ... minus [hole_begin, hole_begin + hole_len): one launch over the two boundary planes of a slab
     int zero;  // always 0; read from the global-memory copy of this block to build values ptxas cannot re-materialise
 };
 

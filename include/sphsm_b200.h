@@ -143,6 +143,15 @@ int sphsm_step(sphsm_handle *h, int nsteps);
 int sphsm_stage(sphsm_handle *h, int stage);
 int sphsm_sync(sphsm_handle *h);
 
+/* Asynchronous forms of the per-frame I/O (what main.cpp does through Get_Paticles() every frame: write stim / fixed,
+ * read pos).  They return once the work is queued: the host arrays should be page-locked (otherwise the copies do not
+ * overlap) and must not be touched until sphsm_io_wait or sphsm_sync returns.  Copies run on dedicated streams in both
+ * directions while the compute stream keeps stepping; each call orders itself after the previous call of its kind. */
+int sphsm_set_masks_async(sphsm_handle *h, const uint8_t *fixed, const float *stim, int n);
+int sphsm_download_positions_async(sphsm_handle *h, float *xyz, int n);
+int sphsm_download_owned_async(sphsm_handle *h, int *ids, float *xyz, int cap, int *count);
+int sphsm_io_wait(sphsm_handle *h);
+
 int sphsm_num_particles(sphsm_handle *h);  /* Get_Particle_Number, h:148 */
 int sphsm_num_cells(sphsm_handle *h);      /* Number_Cells, cpp:37 */
 int sphsm_grid_size(sphsm_handle *h, int out3[3]); /* Grid_Size, cpp:32-35 */

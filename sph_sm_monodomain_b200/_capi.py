@@ -54,6 +54,10 @@ SYMBOLS = {
     "sphsm_step": (C.c_int, [_H, C.c_int]),
     "sphsm_stage": (C.c_int, [_H, C.c_int]),
     "sphsm_sync": (C.c_int, [_H]),
+    "sphsm_set_masks_async": (C.c_int, [_H, _U8P, _FP, C.c_int]),
+    "sphsm_download_positions_async": (C.c_int, [_H, _FP, C.c_int]),
+    "sphsm_download_owned_async": (C.c_int, [_H, _IP, _FP, C.c_int, _IP]),
+    "sphsm_io_wait": (C.c_int, [_H]),
     "sphsm_num_particles": (C.c_int, [_H]),
     "sphsm_num_cells": (C.c_int, [_H]),
     "sphsm_grid_size": (C.c_int, [_H, _IP]),

@@ -65,6 +65,13 @@ struct sphsm_handle {
     float *scratch = nullptr;
     uint8_t *d_aos = nullptr;
     size_t aos_cap_bytes = 0;
+    // asynchronous I/O (sphsm_*_async): copy streams beside the compute stream, their own device staging
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_in_ready = nullptr, ev_in_free = nullptr, ev_out_ready = nullptr, ev_out_done = nullptr;
+    float *io_in_f = nullptr, *io_out_f = nullptr;
+    uint8_t *io_in_b = nullptr;
+    int *io_out_i = nullptr;
+    size_t io_in_cap = 0, io_out_cap = 0;
     float *d_tmp = nullptr;  // staging for position lists (stim_mesh / stim_cube / init_fluid)
     size_t tmp_cap = 0;
     int *d_itmp = nullptr;
@@ -322,6 +329,9 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_meta, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t *e : {&h->ev_in_ready, &h->ev_in_free, &h->ev_out_ready, &h->ev_out_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming));
     h->launch_stream = h->stream;
@@ -376,6 +386,11 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_meta) cudaEventDestroy(h->ev_meta);
+    for (cudaEvent_t e : {h->ev_in_ready, h->ev_in_free, h->ev_out_ready, h->ev_out_done})
+        if (e) cudaEventDestroy(e);
+    if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+    if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
+    cudaFree(h->io_in_f); cudaFree(h->io_in_b); cudaFree(h->io_out_f); cudaFree(h->io_out_i);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
     if (h->ev_int) cudaEventDestroy(h->ev_int);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -736,6 +751,102 @@ extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const floa
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     if (fixed) h->rest_dirty = true;
+    return SPHSM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Asynchronous I/O.  The host arrays must be page-locked for the copies to overlap and must stay untouched until
+// sphsm_io_wait (or sphsm_sync) returns.  Input copies run on their own stream into their own staging and the kernel that
+// applies them waits for the copy; output is gathered on the compute stream and copied out on a second copy stream, so a
+// caller that loops { set_masks_async; step; download_*_async } has step k+1 computing while the results of step k cross
+// PCIe one way and the inputs of step k+2 cross it the other way.
+static int ensure_io_in(sphsm_handle *h, size_t n) {
+    if (h->io_in_cap >= n) return SPHSM_OK;
+    CU(cudaStreamSynchronize(h->h2d_stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->io_in_f); cudaFree(h->io_in_b);
+    h->io_in_f = nullptr; h->io_in_b = nullptr; h->io_in_cap = 0;
+    CU(cudaMalloc(&h->io_in_f, n * sizeof(float)));
+    CU(cudaMalloc(&h->io_in_b, n));
+    h->io_in_cap = n;
+    return SPHSM_OK;
+}
+static int ensure_io_out(sphsm_handle *h, size_t n) {
+    if (h->io_out_cap >= n) return SPHSM_OK;
+    CU(cudaStreamSynchronize(h->d2h_stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->io_out_f); cudaFree(h->io_out_i);
+    h->io_out_f = nullptr; h->io_out_i = nullptr; h->io_out_cap = 0;
+    CU(cudaMalloc(&h->io_out_f, n * 3 * sizeof(float)));
+    CU(cudaMalloc(&h->io_out_i, n * sizeof(int)));
+    h->io_out_cap = n;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_set_masks_async(sphsm_handle *h, const uint8_t *fixed, const float *stim, int n) {
+    if (!h || n != (h->dp.slab_on ? h->n_global : h->n)) return fail(h, SPHSM_ERR_INVALID, "set_masks needs exactly num_particles entries");
+    if (n == 0 || (!fixed && !stim)) return SPHSM_OK;
+    CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if ((rc = ensure_io_in(h, (size_t)n)) != 0) return rc;
+    CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_in_free, 0));  // the previous call's kernel has consumed the staging
+    if (stim) CU(cudaMemcpyAsync(h->io_in_f, stim, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+    if (fixed) CU(cudaMemcpyAsync(h->io_in_b, fixed, (size_t)n, cudaMemcpyHostToDevice, h->h2d_stream));
+    CU(cudaEventRecord(h->ev_in_ready, h->h2d_stream));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_in_ready, 0));
+    if (h->n > 0)
+        LAUNCH(k_set_masks, cdiv(h->n, 256), 256, h->n, h->cur, fixed ? (const uint8_t *)h->io_in_b : nullptr, stim ? h->io_in_f : nullptr,
+               h->prm.diagnostics);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_in_free, h->stream));
+    if (fixed) h->rest_dirty = true;
+    return SPHSM_OK;
+}
+
+static int io_copy_out(sphsm_handle *h, int *ids, float *xyz, size_t count) {
+    CU(cudaEventRecord(h->ev_out_ready, h->stream));
+    CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_out_ready, 0));
+    if (ids) CU(cudaMemcpyAsync(ids, h->io_out_i, count * sizeof(int), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CU(cudaMemcpyAsync(xyz, h->io_out_f, count * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CU(cudaEventRecord(h->ev_out_done, h->d2h_stream));
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_download_positions_async(sphsm_handle *h, float *xyz, int n) {
+    if (!h || !xyz || n < 0) return SPHSM_ERR_INVALID;
+    if (h->dp.slab_on) return fail(h, SPHSM_ERR_INVALID, "slab mode: use sphsm_download_owned_async");
+    if (n > h->n) return SPHSM_ERR_INVALID;
+    if (n == 0) return SPHSM_OK;
+    CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if ((rc = ensure_io_out(h, (size_t)h->n)) != 0) return rc;
+    CU(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));  // the previous copy has left the staging
+    LAUNCH(k_positions_out, cdiv(h->n, 256), 256, 0, h->n, h->cur, h->io_out_f);
+    CU(cudaGetLastError());
+    return io_copy_out(h, nullptr, xyz, (size_t)n);
+}
+
+extern "C" int sphsm_download_owned_async(sphsm_handle *h, int *ids, float *xyz, int cap, int *count) {
+    if (!h || !ids || !xyz || !count || cap < 0) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    const int first = h->dp.own_begin, nown = h->dp.own_end - h->dp.own_begin;
+    *count = nown;
+    if (nown > cap) return fail(h, SPHSM_ERR_CAPACITY, "output arrays smaller than the number of owned particles");
+    if (nown == 0) return SPHSM_OK;
+    int rc;
+    if ((rc = ensure_io_out(h, (size_t)std::max(nown, h->prm.capacity / std::max(h->nranks, 1) + 65536))) != 0) return rc;
+    if ((size_t)nown > h->io_out_cap && (rc = ensure_io_out(h, (size_t)nown)) != 0) return rc;
+    CU(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));
+    LAUNCH(k_mg_owned_out, cdiv(nown, 256), 256, first, nown, h->cur, h->io_out_i, h->io_out_f);
+    CU(cudaGetLastError());
+    return io_copy_out(h, ids, xyz, (size_t)nown);
+}
+
+extern "C" int sphsm_io_wait(sphsm_handle *h) {
+    if (!h) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    CU(cudaStreamSynchronize(h->h2d_stream));
+    CU(cudaStreamSynchronize(h->d2h_stream));
     return SPHSM_OK;
 }
 
@@ -1137,7 +1248,9 @@ extern "C" int sphsm_stage(sphsm_handle *h, int stage) {
 extern "C" int sphsm_sync(sphsm_handle *h) {
     if (!h) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
+    CU(cudaStreamSynchronize(h->h2d_stream));
     CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->d2h_stream));
     CU(cudaGetLastError());
     return SPHSM_OK;
 }

@@ -132,6 +132,22 @@ class Sim:
         self._ck(self.lib.sphsm_set_masks(self.h, None if f is None else f.ctypes.data_as(C.POINTER(C.c_uint8)),
                                           None if s is None else _fp(s), n))
 
+    def set_masks_async(self, fixed=None, stim=None):
+        """sphsm_set_masks_async: the arrays (ideally page-locked) must stay alive and untouched until io_wait() / sync()."""
+        n = len(fixed) if fixed is not None else (len(stim) if stim is not None else self.n)
+        assert fixed is None or (fixed.dtype == np.uint8 and fixed.flags.c_contiguous)
+        assert stim is None or (stim.dtype == np.float32 and stim.flags.c_contiguous)
+        self._ck(self.lib.sphsm_set_masks_async(self.h, None if fixed is None else fixed.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                None if stim is None else _fp(stim), n))
+
+    def download_positions_async(self, out):
+        """sphsm_download_positions_async into `out` ((n, 3) float32, ideally page-locked); valid after io_wait() / sync()."""
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size >= 3 * self.n
+        self._ck(self.lib.sphsm_download_positions_async(self.h, _fp(out), self.n))
+
+    def io_wait(self):
+        self._ck(self.lib.sphsm_io_wait(self.h))
+
     def set_fields(self, **fields):
         """Overwrite per-particle fields (what reference callers do by writing through Get_Paticles())."""
         if set(fields) <= {"fixed", "stim"}:

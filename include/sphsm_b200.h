@@ -152,6 +152,12 @@ int sphsm_download_positions_async(sphsm_handle *h, float *xyz, int n);
 int sphsm_download_owned_async(sphsm_handle *h, int *ids, float *xyz, int cap, int *count);
 int sphsm_io_wait(sphsm_handle *h);
 
+/* Snapshot / restart (the reference has none).  The file holds the tunable parameters and every particle in the
+ * reference's Particle layout (SPHSM_PARTICLE_STRIDE bytes, all 33 fields, original order) plus the step counter;
+ * sphsm_load_state restores them into an existing handle of sufficient capacity and the same world / kernel size. */
+int sphsm_save_state(sphsm_handle *h, const char *path);
+int sphsm_load_state(sphsm_handle *h, const char *path);
+
 int sphsm_num_particles(sphsm_handle *h);  /* Get_Particle_Number, h:148 */
 int sphsm_num_cells(sphsm_handle *h);      /* Number_Cells, cpp:37 */
 int sphsm_grid_size(sphsm_handle *h, int out3[3]); /* Grid_Size, cpp:32-35 */

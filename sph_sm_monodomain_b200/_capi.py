@@ -58,6 +58,8 @@ SYMBOLS = {
     "sphsm_download_positions_async": (C.c_int, [_H, _FP, C.c_int]),
     "sphsm_download_owned_async": (C.c_int, [_H, _IP, _FP, C.c_int, _IP]),
     "sphsm_io_wait": (C.c_int, [_H]),
+    "sphsm_save_state": (C.c_int, [_H, C.c_char_p]),
+    "sphsm_load_state": (C.c_int, [_H, C.c_char_p]),
     "sphsm_num_particles": (C.c_int, [_H]),
     "sphsm_num_cells": (C.c_int, [_H]),
     "sphsm_grid_size": (C.c_int, [_H, _IP]),

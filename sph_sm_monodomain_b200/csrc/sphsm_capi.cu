@@ -755,6 +755,66 @@ extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const floa
 }
 
 // ---------------------------------------------------------------------------------------------------
+// State snapshot / restart (the reference has none).  File = header + sphsm_params + the particles in
+// the reference's own Particle layout (132 B, all 33 fields, original order), i.e. exactly what Get_Paticles() shows.
+struct SnapshotHeader {
+    char magic[8];  // "SPHSMB2\0"
+    uint32_t version, header_bytes, params_bytes, stride;
+    int32_t n, total_steps;
+};
+extern "C" int sphsm_save_state(sphsm_handle *h, const char *path) {
+    if (!h || !path) return SPHSM_ERR_INVALID;
+    if (h->dp.slab_on) return fail(h, SPHSM_ERR_INVALID, "snapshots are written from a single-GPU handle");
+    std::vector<uint8_t> buf((size_t)std::max(h->n, 1) * SPHSM_PARTICLE_STRIDE);
+    int rc = h->n > 0 ? sphsm_download_aos(h, buf.data(), h->n, SPHSM_PARTICLE_STRIDE) : SPHSM_OK;
+    if (rc) return rc;
+    SnapshotHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    memcpy(hd.magic, "SPHSMB2", 8);
+    hd.version = 1; hd.header_bytes = sizeof(hd); hd.params_bytes = sizeof(sphsm_params); hd.stride = SPHSM_PARTICLE_STRIDE;
+    hd.n = h->n; hd.total_steps = h->total_steps;
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(h, SPHSM_ERR_INVALID, "cannot open the snapshot file for writing");
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && fwrite(&h->prm, sizeof(sphsm_params), 1, f) == 1 &&
+              (h->n == 0 || fwrite(buf.data(), (size_t)h->n * SPHSM_PARTICLE_STRIDE, 1, f) == 1);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? SPHSM_OK : fail(h, SPHSM_ERR_INVALID, "short write on the snapshot file");
+}
+// Restores particles, tunable parameters and the step counter into an existing handle (its capacity, device and world
+// stay its own: the snapshot must fit, and its world must match).
+extern "C" int sphsm_load_state(sphsm_handle *h, const char *path) {
+    if (!h || !path) return SPHSM_ERR_INVALID;
+    if (h->dp.slab_on) return fail(h, SPHSM_ERR_INVALID, "load the snapshot before sphsm_comm_set_slab");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(h, SPHSM_ERR_INVALID, "cannot open the snapshot file");
+    SnapshotHeader hd;
+    sphsm_params sp;
+    int rc = SPHSM_OK;
+    std::vector<uint8_t> buf;
+    if (fread(&hd, sizeof(hd), 1, f) != 1 || memcmp(hd.magic, "SPHSMB2", 8) != 0 || hd.version != 1 || hd.header_bytes != sizeof(hd) ||
+        hd.params_bytes != sizeof(sphsm_params) || hd.stride != SPHSM_PARTICLE_STRIDE || hd.n < 0)
+        rc = fail(h, SPHSM_ERR_INVALID, "not a snapshot of this library version");
+    else if (fread(&sp, sizeof(sp), 1, f) != 1)
+        rc = fail(h, SPHSM_ERR_INVALID, "truncated snapshot");
+    else if (hd.n > h->prm.capacity)
+        rc = fail(h, SPHSM_ERR_CAPACITY, "snapshot holds more particles than this handle's capacity");
+    else if (sp.world[0] != h->prm.world[0] || sp.world[1] != h->prm.world[1] || sp.world[2] != h->prm.world[2] || sp.kernel_h != h->prm.kernel_h)
+        rc = fail(h, SPHSM_ERR_INVALID, "snapshot was taken in a different world / kernel size");
+    else {
+        buf.resize((size_t)std::max(hd.n, 1) * SPHSM_PARTICLE_STRIDE);
+        if (hd.n > 0 && fread(buf.data(), (size_t)hd.n * SPHSM_PARTICLE_STRIDE, 1, f) != 1) rc = fail(h, SPHSM_ERR_INVALID, "truncated snapshot");
+    }
+    fclose(f);
+    if (rc) return rc;
+    sp.device = h->prm.device; sp.capacity = h->prm.capacity; sp.slab_axis = h->prm.slab_axis; sp.strict = h->prm.strict;
+    sp.diagnostics = h->prm.diagnostics;
+    if ((rc = sphsm_set_params(h, &sp)) != 0) return rc;
+    if ((rc = sphsm_upload_aos(h, buf.data(), hd.n, SPHSM_PARTICLE_STRIDE)) != 0) return rc;
+    h->total_steps = hd.total_steps;
+    return SPHSM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Asynchronous I/O.  The host arrays must be page-locked for the copies to overlap and must stay untouched until
 // sphsm_io_wait (or sphsm_sync) returns.  Input copies run on their own stream into their own staging and the kernel that
 // applies them waits for the copy; output is gathered on the compute stream and copied out on a second copy stream, so a
@@ -1595,18 +1655,22 @@ static int nccl_exchange2(sphsm_handle *h, cudaStream_t st) {
         NC(g_nccl.Send(h->cur.S + ob, (size_t)(h->b2 - ob) * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
         NC(g_nccl.Recv(h->cur.V, (size_t)ob * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
         NC(g_nccl.Recv(h->cur.S, (size_t)ob * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
-        NC(g_nccl.Send(h->cur.VN + ob, (size_t)(h->b2 - ob), NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
-        NC(g_nccl.Recv(h->cur.VN, (size_t)ob, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
     }
     if (h->rank < h->nranks - 1) {
         NC(g_nccl.Send(h->cur.V + h->b3, (size_t)(oe - h->b3) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
         NC(g_nccl.Send(h->cur.S + h->b3, (size_t)(oe - h->b3) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
         NC(g_nccl.Recv(h->cur.V + oe, (size_t)(n - oe) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
         NC(g_nccl.Recv(h->cur.S + oe, (size_t)(n - oe) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
-        NC(g_nccl.Send(h->cur.VN + h->b3, (size_t)(oe - h->b3), NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
-        NC(g_nccl.Recv(h->cur.VN + oe, (size_t)(n - oe), NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
     }
     NC(g_nccl.GroupEnd());
+    const int halo = ob + (n - oe);  // VN (the dense copy of V.w) of the halo slots is rebuilt locally
+    if (halo > 0) {
+        cudaStream_t keep = h->launch_stream;
+        h->launch_stream = st;
+        int rc = [&]() -> int { LAUNCH(k_mg_halo_vn, cdiv(halo, 256), 256, ob, oe, n - oe, h->cur.V, h->cur.VN); return SPHSM_OK; }();
+        h->launch_stream = keep;
+        if (rc) return rc;
+    }
     return SPHSM_OK;
 }
 
@@ -1726,10 +1790,11 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 h->launch_stream = h->stream;
                 if (rc) return rc;
                 CU(cudaEventRecord(h->ev_bnd, h->side_stream));
-                if ((rc = nccl_exchange2(h, h->side_stream)) != 0) return rc;
-                if ((rc = launch_pass_a(h, h->b2, h->b3)) != 0) return rc;
+                if ((rc = launch_pass_a(h, h->b2, h->b3)) != 0) return rc;  // (queued before the NCCL calls: they take host time)
                 CU(cudaEventRecord(h->ev_int, h->stream));
-                return SPHSM_OK;
+                CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
+                if ((rc = launch_pass_b(h, h->b2, h->b3, diag)) != 0) return rc;
+                return nccl_exchange2(h, h->side_stream);
             }
             if ((rc = launch_pass_a(h, ob, oe)) != 0) return rc;
             if (h->gt) h->gt->end_group(KG_PASS_A);
@@ -1740,9 +1805,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             if (h->gt) h->gt->end_group(KG_OTHER);  // exchange 2
             const int ob = h->dp.own_begin, oe = h->dp.own_end;
             if (h->split) {  // interior planes need no halo record; the boundary planes wait for exchange 2 (stream order)
-                CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
-                if ((rc = launch_pass_b(h, h->b2, h->b3, diag)) != 0) return rc;
-                CU(cudaStreamWaitEvent(h->side_stream, h->ev_int, 0));
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_int, 0));  // (pass B's interior was queued in phase 4)
                 h->launch_stream = h->side_stream;
                 rc = launch_pass_b(h, ob, oe, diag, h->b2, h->b3);
                 h->launch_stream = h->stream;

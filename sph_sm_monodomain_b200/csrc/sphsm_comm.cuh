@@ -125,6 +125,15 @@ __global__ void k_mg_meta(const int *__restrict__ cell_start, int num_cells, int
     meta[7] = 0;
 }
 
+// exchange 2 carries V = (inter_vel, m/dens) and S; the dense copy of V.w that pass B's phase 1 gathers is rebuilt here for
+// the two halo ranges [0, n_left) and [right_begin, right_begin + n_right)
+__global__ void __launch_bounds__(256) k_mg_halo_vn(int n_left, int right_begin, int n_right, const float4 *__restrict__ V, float *__restrict__ VN) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_left + n_right) return;
+    const int s = k < n_left ? k : right_begin + (k - n_left);
+    VN[s] = V[s].w;
+}
+
 // compact (id, xyz) of the owned slots for sphsm_download_owned
 __global__ void __launch_bounds__(256) k_mg_owned_out(int first, int count, Arrays a, int *__restrict__ ids, float *__restrict__ xyz) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;

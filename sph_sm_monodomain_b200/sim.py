@@ -148,6 +148,12 @@ class Sim:
     def io_wait(self):
         self._ck(self.lib.sphsm_io_wait(self.h))
 
+    def save_state(self, path):
+        self._ck(self.lib.sphsm_save_state(self.h, str(path).encode()))
+
+    def load_state(self, path):
+        self._ck(self.lib.sphsm_load_state(self.h, str(path).encode()))
+
     def set_fields(self, **fields):
         """Overwrite per-particle fields (what reference callers do by writing through Get_Paticles())."""
         if set(fields) <= {"fixed", "stim"}:

@@ -239,3 +239,37 @@ def test_async_io_matches_sync(Sim):
     b.io_wait()
     for k in range(6):
         assert np.array_equal(outs[k], ref[k]), k
+
+
+@pytest.mark.parametrize("strict", [True, False], ids=["strict", "fast"])
+def test_snapshot_restart(Sim, tmp_path, strict):
+    """save_state / load_state: a run restarted from a snapshot continues like the uninterrupted one — bit for bit in strict
+    mode (sequential sums in original particle order); within 1e-6 of the field scale on the fast path, whose moment sums
+    are grouped by slot order (the restarted run begins in original order, the uninterrupted one in cell order)."""
+    g, kw = load_golden("lattice_24x10x12")
+    pos = g["positions"]
+    a = Sim(strict=strict, **kw)
+    a.Init_Fluid(pos)
+    a.set_fields(fixed=g["init.fixed"], stim=g["init.stim"])
+    a.add_viscosity(0.25)
+    a.Animation(7)
+    path = tmp_path / "state.sphsm"
+    a.save_state(path)
+    a.Animation(9)
+    b = Sim(strict=strict, **kw)
+    b.load_state(path)
+    assert b.n == a.n and b.lib.sphsm_total_time_steps(b.h) == 7
+    assert b.get_params().mu == a.get_params().mu
+    b.Animation(9)
+    pa, pb = a.particles(), b.particles()
+    for f in ("pos", "vel", "dens", "Vm", "Iion", "w", "stim", "fixed", "orig", "mass"):
+        if strict:
+            assert bits_equal(pa[f], pb[f]), f
+        else:
+            scale = max(1e-30, float(np.abs(pa[f].astype(np.float64)).max()))
+            assert float(np.abs(pa[f].astype(np.float64) - pb[f].astype(np.float64)).max()) <= 1e-6 * scale, f
+    small = Sim(capacity=100, world=kw["world"])
+    with pytest.raises(Exception):
+        small.load_state(path)  # more particles than capacity
+    with pytest.raises(Exception):
+        b.load_state(tmp_path / "missing.sphsm")

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
@@ -51,6 +52,10 @@ struct sphsm_handle {
     cudaStream_t side_stream = nullptr;    // slab step: moment sums + allreduce + solve run here, beside the sort
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_meta = nullptr, ev_bnd = nullptr, ev_int = nullptr;
     bool moments_forked = false;
+    bool allreduce_pending = false;        // slab step: the forked sums still need their allreduce (issued after exchange 1 on a shared communicator)
+    cudaEvent_t pev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // SPHSM_HOST_PROF: device-side brackets
+    double pacc[4] = {0, 0, 0, 0};
+    double meta_wait_us = 0.0;             // SPHSM_HOST_PROF: host time spent waiting for the plane boundaries
     bool reordered = false;                // slab step: the gather was queued before the plane boundaries reached the host
     bool split = false;                    // slab step: exchange 2 in flight on the side stream beside the interior planes
     Arrays cur{}, alt{};
@@ -93,6 +98,8 @@ struct sphsm_handle {
     int comm_mode = 0;        // 0 none, 1 NCCL (one process per GPU), 2 local group (virtual ranks on one device, for tests)
     int nranks = 1, rank = 0;
     void *nccl_comm = nullptr;
+    void *nccl_comm_red = nullptr;  // second communicator (ncclCommSplit) for the moment allreduce: NCCL runs one communicator's
+                                    // operations in issue order, which queued the allreduce behind exchange 1 (or the reverse)
     bool slab_applied = false;
     int send_cap = 0;         // particles per exchange-1 message
     int alloc_n = 0;          // slots allocated per array (capacity + room for two halo messages in slab mode)
@@ -314,7 +321,12 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     // slab mode appends up to two halo messages behind the local particles before every sort: room for them
     if (p->slab_axis >= 0) {
         int hc = p->reserved[0];  // halo capacity override (particles per message)
-        if (hc <= 0) hc = (int)(pow((double)p->capacity, 2.0 / 3.0)) + 4096;
+        if (hc <= 0) {
+            // default: three times the average population of a cell plane across the slab axis at full capacity (a cell
+            // plane of a regular lattice holds one OR two lattice planes), plus slack for migrants
+            const double planes = std::max(1.0, ceil((double)p->world[p->slab_axis] / (double)p->kernel_h));
+            hc = (int)std::min((double)p->capacity, 3.0 * (double)p->capacity / planes) + 4096;
+        }
         h->send_cap = hc;
     }
     h->alloc_n = p->capacity + 2 * h->send_cap;
@@ -379,6 +391,7 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     for (int k = 0; k < 2; k++) { cudaFree(h->msg_send[k]); cudaFree(h->msg_recv[k]); }
     cudaFree(h->d_err); cudaFree(h->d_meta);
     if (h->h_meta) cudaFreeHost(h->h_meta);
+    if (h->nccl_comm_red && h->nccl_comm_red != h->nccl_comm && g_nccl_destroy) g_nccl_destroy(h->nccl_comm_red);
     if (h->nccl_comm && g_nccl_destroy) g_nccl_destroy(h->nccl_comm);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ev_step0) cudaEventDestroy(h->ev_step0);
@@ -1448,6 +1461,7 @@ struct NcclApi {
     void *lib = nullptr;
     int (*GetUniqueId)(nccl_unique_id *) = nullptr;
     int (*CommInitRank)(void **, int, nccl_unique_id, int) = nullptr;
+    int (*CommSplit)(void *, int, int, void **, void *) = nullptr;  // optional (NCCL >= 2.18)
     int (*CommDestroy)(void *) = nullptr;
     int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
@@ -1470,6 +1484,7 @@ static int load_nccl(sphsm_handle *h) {
     auto sym = [&](const char *nm) { void *f = dlsym(lib, nm); if (!f) ok = false; return f; };
     g_nccl.GetUniqueId = (int (*)(nccl_unique_id *))sym("ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void **, int, nccl_unique_id, int))sym("ncclCommInitRank");
+    g_nccl.CommSplit = (int (*)(void *, int, int, void **, void *))dlsym(lib, "ncclCommSplit");
     g_nccl.CommDestroy = (int (*)(void *))sym("ncclCommDestroy");
     g_nccl.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))sym("ncclSend");
     g_nccl.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))sym("ncclRecv");
@@ -1529,6 +1544,8 @@ extern "C" int sphsm_comm_init(sphsm_handle *h, int nranks, int rank, const void
     nccl_unique_id id;
     memcpy(&id, id128, sizeof id);
     NC(g_nccl.CommInitRank(&h->nccl_comm, nranks, id, rank));
+    h->nccl_comm_red = h->nccl_comm;
+    if (g_nccl.CommSplit && !getenv("SPHSM_ONE_COMM")) NC(g_nccl.CommSplit(h->nccl_comm, 0, rank, &h->nccl_comm_red, nullptr));
     h->comm_mode = 1; h->nranks = nranks; h->rank = rank;
     return comm_alloc(h);
 }
@@ -1551,6 +1568,12 @@ extern "C" int sphsm_comm_init_local(sphsm_handle **hs, int nranks) {
 }
 
 // read the plane boundaries back (one 32-byte copy + stream sync) and set n / owned range from them
+static bool g_host_prof_early() { static const bool v = getenv("SPHSM_HOST_PROF") != nullptr; return v; }
+static double now_us_early() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
 static int slab_meta_launch(sphsm_handle *h) {
     const DevParams &d = h->dp;
     LAUNCH(k_mg_meta, 1, 32, h->cell_start, d.num_cells, d.ga * d.gb, d.gcl, h->d_err, h->d_meta);
@@ -1559,7 +1582,9 @@ static int slab_meta_launch(sphsm_handle *h) {
     return SPHSM_OK;
 }
 static int slab_meta_read(sphsm_handle *h) {
+    const double tw = g_host_prof_early() ? now_us_early() : 0.0;
     CU(cudaEventSynchronize(h->ev_meta));  // (not the stream: work queued behind the read-back keeps running)
+    if (tw != 0.0) h->meta_wait_us += now_us_early() - tw;
     const int *m = h->h_meta;
     if (m[5]) return fail(h, SPHSM_ERR_COMM, "a particle crossed more than one cell plane in one step (or left the slab window)");
     if (m[6]) return fail(h, SPHSM_ERR_COMM, "halo message overflow: raise params.reserved[0] (halo capacity)");
@@ -1629,7 +1654,7 @@ extern "C" int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int c
 // ---- collectives: NCCL (one process per GPU) --------------------------------------------------------------------
 static int comm_allreduce(sphsm_handle *h, int count) {
     if (h->comm_mode != 1 || h->nranks == 1) return SPHSM_OK;  // single GPU; the local group sums between phases
-    NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm, h->launch_stream));
+    NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm_red, h->launch_stream));
     return SPHSM_OK;
 }
 static int nccl_exchange1(sphsm_handle *h) {
@@ -1678,6 +1703,7 @@ static int nccl_exchange2(sphsm_handle *h, cudaStream_t st) {
 enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE };
 static const int MG_PHASES = 6;
 
+static int mg_forked_allreduce(sphsm_handle *h);
 static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
     const bool diag = h->prm.diagnostics != 0;
     const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
@@ -1701,6 +1727,11 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 h->launch_stream = h->stream;
                 if (rc) return rc;
                 h->moments_forked = true;
+                h->allreduce_pending = true;
+                if (h->nccl_comm_red != h->nccl_comm) {  // own communicator: nothing to queue behind
+                    if ((rc = mg_forked_allreduce(h)) != 0) return rc;
+                    h->allreduce_pending = false;
+                }
             }
             CU(cudaMemsetAsync(h->msg_send[0], 0, 16, h->stream));
             CU(cudaMemsetAsync(h->msg_send[1], 0, 16, h->stream));
@@ -1794,7 +1825,10 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 CU(cudaEventRecord(h->ev_int, h->stream));
                 CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
                 if ((rc = launch_pass_b(h, h->b2, h->b3, diag)) != 0) return rc;
-                return nccl_exchange2(h, h->side_stream);
+                if (g_host_prof_early() && h->pev[4]) CU(cudaEventRecord(h->pev[4], h->side_stream));
+                rc = nccl_exchange2(h, h->side_stream);
+                if (g_host_prof_early() && h->pev[5]) CU(cudaEventRecord(h->pev[5], h->side_stream));
+                return rc;
             }
             if ((rc = launch_pass_a(h, ob, oe)) != 0) return rc;
             if (h->gt) h->gt->end_group(KG_PASS_A);
@@ -1848,18 +1882,66 @@ static int mg_forked_allreduce(sphsm_handle *h) {
     return SPHSM_OK;
 }
 
+// SPHSM_HOST_PROF=1: host-side time of the slab step per phase (kernel launches / NCCL calls / the read-back wait), printed
+// by rank 0 every 64 steps — tells a launch-bound step from a device-bound one
+static const bool g_host_prof = getenv("SPHSM_HOST_PROF") != nullptr;
+static double now_us() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
 static int mg_step_nccl(sphsm_handle *h) {
     int rc, coll, count;
     if ((rc = mg_check(h)) != 0) return rc;
+    static double acc[MG_PHASES + 1][2];
+    static int steps_seen = 0;
     for (int ph = 0; ph < MG_PHASES; ph++) {
+        const double t0 = g_host_prof ? now_us() : 0.0;
         if ((rc = mg_phase(h, ph, &coll, &count)) != 0) return rc;
+        const double t1 = g_host_prof ? now_us() : 0.0;
         if (coll == COLL_EXCH1) {
+            if (g_host_prof) {
+                for (int k = 0; k < 8; k++)
+                    if (!h->pev[k]) CU(cudaEventCreate(&h->pev[k]));
+                CU(cudaEventRecord(h->pev[0], h->stream));
+            }
             rc = nccl_exchange1(h);
-            if (!rc && h->moments_forked) rc = mg_forked_allreduce(h);
+            if (g_host_prof) CU(cudaEventRecord(h->pev[1], h->stream));
+            if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[2], h->side_stream));
+            if (!rc && h->moments_forked && h->allreduce_pending) rc = mg_forked_allreduce(h);
+            h->allreduce_pending = false;
+            if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[3], h->side_stream));
         }
         else if (coll == COLL_ALLREDUCE) rc = comm_allreduce(h, count);
         else if (coll == COLL_EXCH2) rc = nccl_exchange2(h, h->stream);
         if (rc) return rc;
+        if (g_host_prof) {
+            acc[ph][0] += t1 - t0;
+            acc[ph][1] += now_us() - t1;
+        }
+    }
+    if (g_host_prof && h->pev[5] && h->split) {  // device-side durations of the three collectives (this serialises the steps)
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaStreamSynchronize(h->side_stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->pev[0], h->pev[1]) == cudaSuccess) h->pacc[0] += ms * 1e3;
+        if (cudaEventElapsedTime(&ms, h->pev[2], h->pev[3]) == cudaSuccess) h->pacc[1] += ms * 1e3;
+        if (cudaEventElapsedTime(&ms, h->pev[4], h->pev[5]) == cudaSuccess) h->pacc[2] += ms * 1e3;
+        if (cudaEventElapsedTime(&ms, h->pev[0], h->pev[5]) == cudaSuccess) h->pacc[3] += ms * 1e3;
+        cudaGetLastError();
+    }
+    if (g_host_prof && ++steps_seen % 64 == 0) {
+        fprintf(stderr, "[sphsm dev prof rank %d, cumulative us over %d steps] exch1 %.0f allreduce+solve %.0f exch2+vn %.0f exch1-start..exch2-end %.0f\n",
+                h->rank, steps_seen, h->pacc[0], h->pacc[1], h->pacc[2], h->pacc[3]);
+    }
+    if (g_host_prof && steps_seen % 64 == 0 && h->rank == 0) {
+        fprintf(stderr, "[sphsm host prof, us/step over %d steps] ", steps_seen);
+        double tot = 0;
+        for (int ph = 0; ph < MG_PHASES; ph++) {
+            fprintf(stderr, "ph%d %.1f+%.1f  ", ph, acc[ph][0] / steps_seen, acc[ph][1] / steps_seen);
+            tot += acc[ph][0] + acc[ph][1];
+        }
+        fprintf(stderr, "total %.1f (read-back wait %.1f)\n", tot / steps_seen, h->meta_wait_us / steps_seen);
     }
     return SPHSM_OK;
 }

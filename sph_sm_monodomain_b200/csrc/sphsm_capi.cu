@@ -98,8 +98,7 @@ struct sphsm_handle {
     int comm_mode = 0;        // 0 none, 1 NCCL (one process per GPU), 2 local group (virtual ranks on one device, for tests)
     int nranks = 1, rank = 0;
     void *nccl_comm = nullptr;
-    void *nccl_comm_red = nullptr;  // second communicator (ncclCommSplit) for the moment allreduce: NCCL runs one communicator's
-                                    // operations in issue order, which queued the allreduce behind exchange 1 (or the reverse)
+    void *nccl_comm_red = nullptr;  // communicator of the moment allreduce: nccl_comm, or a split of it (SPHSM_SPLIT_COMM)
     bool slab_applied = false;
     int send_cap = 0;         // particles per exchange-1 message
     int alloc_n = 0;          // slots allocated per array (capacity + room for two halo messages in slab mode)
@@ -322,10 +321,10 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     if (p->slab_axis >= 0) {
         int hc = p->reserved[0];  // halo capacity override (particles per message)
         if (hc <= 0) {
-            // default: three times the average population of a cell plane across the slab axis at full capacity (a cell
+            // default: 2.5 times the average population of a cell plane across the slab axis at full capacity (a cell
             // plane of a regular lattice holds one OR two lattice planes), plus slack for migrants
             const double planes = std::max(1.0, ceil((double)p->world[p->slab_axis] / (double)p->kernel_h));
-            hc = (int)std::min((double)p->capacity, 3.0 * (double)p->capacity / planes) + 4096;
+            hc = (int)std::min((double)p->capacity, 2.5 * (double)p->capacity / planes) + 4096;
         }
         h->send_cap = hc;
     }
@@ -1545,7 +1544,9 @@ extern "C" int sphsm_comm_init(sphsm_handle *h, int nranks, int rank, const void
     memcpy(&id, id128, sizeof id);
     NC(g_nccl.CommInitRank(&h->nccl_comm, nranks, id, rank));
     h->nccl_comm_red = h->nccl_comm;
-    if (g_nccl.CommSplit && !getenv("SPHSM_ONE_COMM")) NC(g_nccl.CommSplit(h->nccl_comm, 0, rank, &h->nccl_comm_red, nullptr));
+    // SPHSM_SPLIT_COMM=1: allreduce on a second communicator.  Off by default: measured at 8 GPUs / 8M it gained nothing (the
+    // allreduce queued behind exchange 1 still ends before the sort does) and the two NCCL kernels then share the SMs.
+    if (g_nccl.CommSplit && getenv("SPHSM_SPLIT_COMM")) NC(g_nccl.CommSplit(h->nccl_comm, 0, rank, &h->nccl_comm_red, nullptr));
     h->comm_mode = 1; h->nranks = nranks; h->rank = rank;
     return comm_alloc(h);
 }

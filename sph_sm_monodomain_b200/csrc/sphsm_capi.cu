@@ -20,6 +20,7 @@
 #include "sphsm_pass2.cuh"
 #include "sphsm_pass3.cuh"
 #include "sphsm_pass4.cuh"
+#include "sphsm_pass5.cuh"
 #include "sphsm_sm.cuh"
 #include "sphsm_sort.cuh"
 #include "sphsm_types.cuh"
@@ -1189,7 +1190,8 @@ static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, in
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
-    if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
+    if (g_pass_gen == 5) LAUNCH(k_pass_a5, cdiv(cdiv(count, 2), PT5), PT5, d, h->d_dp, h->cur, h->cell_start, count);
+    else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
     else if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
     else LAUNCH(k_pass_a3, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
     return SPHSM_OK;
@@ -1199,7 +1201,7 @@ static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hol
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
-    if (g_pass_gen == 4) {
+    if (g_pass_gen == 4 || g_pass_gen == 5) {
         if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
         else LAUNCH(k_pass_b4<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
     } else if (g_pass_gen == 2) {
@@ -1810,7 +1812,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             const int ob = h->dp.own_begin, oe = h->dp.own_end;
             // NCCL mode with at least three owned planes: pass A on the two boundary planes first, their V / S records travel
             // on the side stream while the interior planes are computed here (and pass B's interior after them)
-            h->split = h->comm_mode == 1 && h->nranks > 1 && !h->profiling && h->b2 < h->b3 && g_pass_gen == 4;
+            h->split = h->comm_mode == 1 && h->nranks > 1 && !h->profiling && h->b2 < h->b3 && g_pass_gen >= 4;
             if (h->split) {
                 // side stream (high priority): pass A on the two boundary planes -> exchange 2 -> pass B on them;
                 // main stream: pass A, then pass B on the interior planes.  Cross dependencies: pass B's interior reads the

@@ -75,7 +75,7 @@ __device__ __forceinline__ void load_rows3(const int *__restrict__ mid, int ga, 
 // Sweep the nine stencil rows in the reference's order (cpp:462-464).  `pair(j, two, lofs)` evaluates the candidates j and
 // j+1 (`two` false: j+1 is past the row) and appends the in-range ones at s_list[lofs], lofs += PT; `one(j, lofs)` is the
 // single-candidate form for rows that could overflow the list (dense meshes); `drain(lofs)` consumes the list.
-template <class Pair, class One, class Drain>
+template <int STEP = 2, class Pair, class One, class Drain>
 __device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict__ cell_start, int ga, int gagb, int key0, int cc, unsigned lbase,
                                        unsigned &lofs, Pair &&pair, One &&one, Drain &&drain) {
     const int *center = cell_start + (key0 - 1);
@@ -92,7 +92,10 @@ __device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict
             const int e = cur.e[k];
             if (lofs + (unsigned)(e - j) * LSTEP <= lmax) {
 #pragma unroll 1
-                for (; j < e; j += 2) pair(j, j + 1 < e, lofs);
+                for (; j < e; j += STEP) {
+                    if constexpr (STEP == 2) pair(j, j + 1 < e, lofs);
+                    else pair(j, e, lofs);  // the body masks j+1 .. j+STEP-1 against the row end itself
+                }
             } else {
                 if (lofs == lmax) drain(lofs);  // the unchecked path may have filled the list exactly
 #pragma unroll 1
@@ -109,7 +112,7 @@ __device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict
 
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
-__global__ void __launch_bounds__(PT, 10) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+__global__ void __launch_bounds__(PT, 9) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 const int *__restrict__ cell_start) {
     __shared__ int s_list[LIST_K * PT];
     int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
@@ -130,17 +133,27 @@ __global__ void __launch_bounds__(PT, 10) k_pass_a4(const __grid_constant__ DevP
     int ca, cb, cc;
     if (cell_coords(p, pi.x, pi.y, pi.z, ca, cb, cc)) {
         auto r2_of = [&](const float4 pj) { return dist2_packed(__fadd2_rn(make_float2(pj.x, pj.y), nxy), pj.z + nz); };
-        sweep4(
+        // four candidates per iteration: a lattice row (3-4 candidates) has all its loads in flight at once — the pair loop
+        // left the kernel waiting on L1 (long-scoreboard 9 warps per issue at 87 % L1 data-path utilisation, ncu r01_v7)
+        sweep4<4>(
             p, cell_start, ga, gagb, cell_key(p, ca, cb, cc), cc, lbase, lofs,
-            [&](int j, bool two, unsigned &lo) {
-                const float4 p0 = __ldg(P + j), p1 = __ldg(P + j + 1);
-                const float r0 = r2_of(p0), r1 = r2_of(p1);
+            [&](int j, int e, unsigned &lo) {
+                const float4 p0 = __ldg(P + j), p1 = __ldg(P + j + 1), p2 = __ldg(P + j + 2), p3 = __ldg(P + j + 3);
+                const float r0 = r2_of(p0), r1 = r2_of(p1), r2 = r2_of(p2), r3 = r2_of(p3);
                 if (r0 <= h2) {  // Poly6 support, cpp:151
                     list_put(lo, j);
                     lo += LSTEP;
                 }
-                if (two && r1 <= h2) {
+                if ((j + 1 < e) & (r1 <= h2)) {
                     list_put(lo, j + 1);
+                    lo += LSTEP;
+                }
+                if ((j + 2 < e) & (r2 <= h2)) {
+                    list_put(lo, j + 2);
+                    lo += LSTEP;
+                }
+                if ((j + 3 < e) & (r3 <= h2)) {
+                    list_put(lo, j + 3);
                     lo += LSTEP;
                 }
             },

@@ -229,6 +229,9 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
     if (z >= p.world[2]) { vz *= p.wall_hit; z = __fsub_rn(p.world[2], 0.0001f); }
 }
 
+#ifndef SPHSM_B_STEP
+#define SPHSM_B_STEP 2  // candidates per unchecked iteration of pass B phase 1 (2 or 4; 4 needs 72 registers and measured 686 us against 678)
+#endif
 // pass B: ionic cell model + pressure / viscosity force + SPH Laplacian of Vm + integration and walls
 // (reference cpp:575-593, 515-573, 598-651).  PB = (pos.xyz, Vm) is the neighbour record of this pass.
 template <bool DIAG>
@@ -275,8 +278,20 @@ __global__ void __launch_bounds__(PT, 8) k_pass_b4(const __grid_constant__ DevPa
             acc = on ? t : acc;
             return on && r2 <= sp2;
         };
-        sweep4(
+        sweep4<SPHSM_B_STEP>(
             p, cell_start, ga, gagb, cell_key(p, ca, cb, cc), cc, lbase, lofs,
+#if SPHSM_B_STEP == 4
+            [&](int j, int e, unsigned &lo) {
+                const float4 p0 = __ldg(PB + j), p1 = __ldg(PB + j + 1), p2 = __ldg(PB + j + 2), p3 = __ldg(PB + j + 3);
+                const float v0 = __ldg(VN + j), v1 = __ldg(VN + j + 1), v2 = __ldg(VN + j + 2), v3 = __ldg(VN + j + 3);
+                const bool i0 = cand(p0, v0, true, L), i1 = cand(p1, v1, j + 1 < e, L1);
+                const bool i2 = cand(p2, v2, j + 2 < e, L), i3 = cand(p3, v3, j + 3 < e, L1);
+                if (i0) { list_put(lo, j); lo += LSTEP; }
+                if (i1) { list_put(lo, j + 1); lo += LSTEP; }
+                if (i2) { list_put(lo, j + 2); lo += LSTEP; }
+                if (i3) { list_put(lo, j + 3); lo += LSTEP; }
+            },
+#else
             [&](int j, bool two, unsigned &lo) {
                 const float4 p0 = __ldg(PB + j), p1 = __ldg(PB + j + 1);
                 const float v0 = __ldg(VN + j), v1 = __ldg(VN + j + 1);
@@ -289,6 +304,7 @@ __global__ void __launch_bounds__(PT, 8) k_pass_b4(const __grid_constant__ DevPa
                     lo += LSTEP;
                 }
             },
+#endif
             [&](int j, unsigned &lo) {
                 if (cand(__ldg(PB + j), __ldg(VN + j), true, L)) {
                     list_put(lo, j);

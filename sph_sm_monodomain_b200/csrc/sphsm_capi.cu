@@ -1191,7 +1191,7 @@ static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, in
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
     if (g_pass_gen == 5) LAUNCH(k_pass_a5, cdiv(cdiv(count, 2), PT5), PT5, d, h->d_dp, h->cur, h->cell_start, count);
-    else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
+    else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start);
     else if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
     else LAUNCH(k_pass_a3, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
     return SPHSM_OK;
@@ -1202,8 +1202,8 @@ static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hol
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
     if (g_pass_gen == 4 || g_pass_gen == 5) {
-        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b4<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
     } else if (g_pass_gen == 2) {
         if (diag) LAUNCH(k_pass_b2<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
         else LAUNCH(k_pass_b2<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);

@@ -41,7 +41,11 @@ __device__ __forceinline__ int list_get(unsigned addr) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
-constexpr unsigned LSTEP = 4u * PT;  // bytes between consecutive entries of one lane
+#ifndef SPHSM_PT4
+#define SPHSM_PT4 128  // measured at 8M (pass A / pass B us): 64: 484 / 689, 128: 469 / 678, 256: 497 / 692, 512: 523 / 720
+#endif
+constexpr int PT4 = SPHSM_PT4;        // threads per block of the generation-4 passes
+constexpr unsigned LSTEP = 4u * PT4;  // bytes between consecutive entries of one lane
 // Likewise a gathered array's base pointer: `pinned(ptr, zero)` is ptr + 0 with the zero coming from global memory, formed
 // in PTX so that neither the front end (which would fold it into the index) nor ptxas (which would re-load the kernel
 // parameter with LDC at every use) can take it apart; the gathers are then one IMAD.WIDE + LDG.
@@ -112,10 +116,10 @@ __device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict
 
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
-__global__ void __launch_bounds__(PT, 9) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+__global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 const int *__restrict__ cell_start) {
-    __shared__ int s_list[LIST_K * PT];
-    int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
+    __shared__ int s_list[LIST_K * PT4];
+    int i = p.own_begin + blockIdx.x * PT4 + threadIdx.x;
     if (i >= p.hole_begin) i += p.hole_len;
     if (i >= p.own_end) return;
     const float4 pi = a.P[i];
@@ -235,10 +239,10 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
 // pass B: ionic cell model + pressure / viscosity force + SPH Laplacian of Vm + integration and walls
 // (reference cpp:575-593, 515-573, 598-651).  PB = (pos.xyz, Vm) is the neighbour record of this pass.
 template <bool DIAG>
-__global__ void __launch_bounds__(PT, 8) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+__global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 float4 *__restrict__ Pout, const int *__restrict__ cell_start) {
-    __shared__ int s_list[LIST_K * PT];
-    int i = p.own_begin + blockIdx.x * PT + threadIdx.x;
+    __shared__ int s_list[LIST_K * PT4];
+    int i = p.own_begin + blockIdx.x * PT4 + threadIdx.x;
     if (i >= p.hole_begin) i += p.hole_len;
     if (i >= p.own_end) return;
     const float4 pi = a.P[i];

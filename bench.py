@@ -38,6 +38,10 @@ UNIT = "particle-steps/s"
 # algorithmic bytes per particle — whole fused-minimal step and the fused pass B
 STEP_BYTES_PER_PARTICLE = 244
 PASS_B_BYTES_PER_PARTICLE = 92
+# On one GPU pass B also files the next step's counting-sort input (key 4 B + provisional rank 4 B per particle; the position
+# it hashes is the one it has just integrated, so the hash stage's 12 B position read disappears): 92 + 8.  Slab mode keeps
+# the separate k_cell_count (arrivals are not known yet) and the 92 B figure.
+PASS_B_FUSED_HASH_BYTES = 8
 PASS_B_NAME = "pass_b(cell+force+laplacian+integrate)"
 
 WORKLOADS = {
@@ -247,10 +251,13 @@ def run_ours(args, wl, rank, world_size, local_rank):
     if world_size > 1:
         info = sim.comm_info()
         n_local = info["own_end"] - info["own_begin"]
-    achieved = PASS_B_BYTES_PER_PARTICLE * n_local / (pb_ms * 1e-3) / 1e9
-    roofline = {"kernel": "k_pass_b (fused cell model + force + Laplacian + integration)", "bound": "hbm", "achieved": achieved,
+    pb_bytes = PASS_B_BYTES_PER_PARTICLE + (PASS_B_FUSED_HASH_BYTES if world_size == 1 else 0)
+    achieved = pb_bytes * n_local / (pb_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k_pass_b4 (fused cell model + force + Laplacian + integration"
+                          + (" + next step's cell key / rank / count)" if world_size == 1 else ")"),
+                "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_particle": PASS_B_BYTES_PER_PARTICLE, "ms_per_launch": pb_ms,
+                "algorithmic_bytes_per_particle": pb_bytes, "ms_per_launch": pb_ms,
                 "whole_step": {"achieved": STEP_BYTES_PER_PARTICLE * n_total / (ev_ms / args.steps * 1e-3) / 1e9,
                                "algorithmic_bytes_per_particle": STEP_BYTES_PER_PARTICLE},
                 "kernel_group_ms": groups}

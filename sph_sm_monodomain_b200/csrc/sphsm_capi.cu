@@ -65,6 +65,7 @@ struct sphsm_handle {
     int sorted_buf = 0;  // which keys[] / vals[] hold the sorted result
     uint32_t *cell_count = nullptr, *tile_sums = nullptr;  // counting sort: per-cell counts (kept zero between steps), scan scratch
     bool bounds_ready = false;                             // grid_sort already produced the cell_start table
+    bool counts_ready = false;  // pass B already filed keys / ranks / per-cell counts of the CURRENT positions (single-GPU fast step)
     int *cell_start = nullptr, *slot_of = nullptr;
     SmState *sm = nullptr;
     double *partial = nullptr, *totals = nullptr;
@@ -288,6 +289,7 @@ static int setup_grid_buffers(sphsm_handle *h) {
     h->cell_count = h->tile_sums = nullptr;
     CU(cudaMalloc(&h->cell_count, ((size_t)h->dp.num_cells + 2 + SCAN_IPT) * sizeof(uint32_t)));
     CU(cudaMemset(h->cell_count, 0, ((size_t)h->dp.num_cells + 2 + SCAN_IPT) * sizeof(uint32_t)));
+    h->counts_ready = false;
     CU(cudaMalloc(&h->tile_sums, ((size_t)(h->dp.num_cells + 2) / SCAN_TILE + 2) * sizeof(uint32_t)));
     int bits = 1;
     while ((1ll << bits) < (long long)h->dp.num_cells + 1) bits++;
@@ -617,7 +619,14 @@ static int ensure_aos(sphsm_handle *h, size_t bytes) {
     h->aos_cap_bytes = bytes;
     return SPHSM_OK;
 }
+// positions (or the grid) are about to change behind pass B's back: its pre-filed counts for the next sort are void
+static void drop_counts(sphsm_handle *h) {
+    if (!h->counts_ready) return;
+    h->counts_ready = false;
+    if (h->cell_count) cudaMemsetAsync(h->cell_count, 0, ((size_t)h->dp.num_cells + 2 + SCAN_IPT) * sizeof(uint32_t), h->stream);
+}
 static void state_changed(sphsm_handle *h, bool rest) {
+    drop_counts(h);
     h->grid_valid = false;
     h->slot_of_valid = false;
     h->inter_live = true;
@@ -977,7 +986,8 @@ static bool use_counting_sort(const sphsm_handle *h) {
 static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt) {
     const int n = h->n, m = h->dp.num_cells + 1;  // cells + the limbo bucket
     const int tiles = cdiv(m + 1, SCAN_TILE);
-    LAUNCH(k_cell_count, cdiv(n, 256), 256, h->dp, h->cur.P, h->keys[0], h->keys[1], h->cell_count);
+    if (h->counts_ready) h->counts_ready = false;  // pass B filed keys, ranks and counts of these positions while it held them
+    else LAUNCH(k_cell_count, cdiv(n, 256), 256, h->dp, h->cur.P, h->keys[0], h->keys[1], h->cell_count);
     if (gt) gt->end_group(KG_HASH);
     LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
     LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles);
@@ -993,6 +1003,7 @@ static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt) {
 static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
     const int n = h->n;
     if (use_counting_sort(h)) return grid_sort_counting(h, gt);
+    drop_counts(h);
     h->bounds_ready = false;
     const int passes = h->sort_passes;
     const int tiles = cdiv(n, SORT_TILE);
@@ -1173,6 +1184,7 @@ static int run_stage(sphsm_handle *h, int stage) {
             LAUNCH((k_pass_b<STRICT, PB_FORCE_ONLY>), cdiv(n, 128), 128, h->dp, h->cur, (float4 *)nullptr, h->cell_start);
             break;
         case SPHSM_STAGE_UPDATE:
+            drop_counts(h);
             LAUNCH(k_update<STRICT>, cdiv(n, 256), 256, h->dp, h->cur);
             h->grid_valid = false;
             break;
@@ -1196,14 +1208,15 @@ static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, in
     else LAUNCH(k_pass_a3, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
     return SPHSM_OK;
 }
-static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hole_b = 0, int hole_e = 0) {
+static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hole_b = 0, int hole_e = 0, bool file_counts = false) {
+    uint32_t *nk = file_counts ? h->keys[0] : nullptr, *nr = file_counts ? h->keys[1] : nullptr, *ncnt = file_counts ? h->cell_count : nullptr;
     const int count = end - begin - (hole_e - hole_b);
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
     if (g_pass_gen == 4 || g_pass_gen == 5) {
-        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt);
+        else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt);
     } else if (g_pass_gen == 2) {
         if (diag) LAUNCH(k_pass_b2<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
         else LAUNCH(k_pass_b2<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
@@ -1257,7 +1270,11 @@ static int fused_step(sphsm_handle *h) {
     } else {
         if ((rc = launch_pass_a(h, 0, n)) != 0) return rc;  // single GPU: own range = [0, n)
         gt.end_group(KG_PASS_A);
-        if ((rc = launch_pass_b(h, 0, n, diag)) != 0) return rc;
+        // the counting sort of the NEXT step starts inside pass B: each thread files the key / rank / count of the position it
+        // has just integrated (valid until anything else moves particles: drop_counts)
+        const bool file_counts = g_pass_gen >= 4 && h->comm_mode == 0 && use_counting_sort(h);
+        if ((rc = launch_pass_b(h, 0, n, diag, 0, 0, file_counts)) != 0) return rc;
+        h->counts_ready = file_counts;
     }
     std::swap(h->cur.P, h->alt.P);
     gt.end_group(KG_PASS_B);

@@ -238,9 +238,12 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
 #endif
 // pass B: ionic cell model + pressure / viscosity force + SPH Laplacian of Vm + integration and walls
 // (reference cpp:575-593, 515-573, 598-651).  PB = (pos.xyz, Vm) is the neighbour record of this pass.
+// cell_count != nullptr: the thread also files its particle's NEW position for the next step's counting sort (key, provisional
+// rank in the cell, per-cell count — what k_cell_count does, without re-reading the positions)
 template <bool DIAG>
 __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
-                                                float4 *__restrict__ Pout, const int *__restrict__ cell_start) {
+                                                float4 *__restrict__ Pout, const int *__restrict__ cell_start, uint32_t *__restrict__ next_keys,
+                                                uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count) {
     __shared__ int s_list[LIST_K * PT4];
     int i = p.own_begin + blockIdx.x * PT4 + threadIdx.x;
     if (i >= p.hole_begin) i += p.hole_len;
@@ -355,6 +358,11 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
     Pout[i] = make_float4(x, y, z, pi.w);
     a.VEL[i] = v4;
     a.E[i] = e4;
+    if (cell_count) {
+        const uint32_t key = cell_coords(p, x, y, z, ca, cb, cc) ? (uint32_t)cell_key(p, ca, cb, cc) : (uint32_t)p.num_cells;
+        next_keys[i] = key;
+        next_rank[i] = atomicAdd(&cell_count[key], 1u);
+    }
 }
 
 }  // namespace sphsm

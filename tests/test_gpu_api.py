@@ -273,3 +273,40 @@ def test_snapshot_restart(Sim, tmp_path, strict):
         small.load_state(path)  # more particles than capacity
     with pytest.raises(Exception):
         b.load_state(tmp_path / "missing.sphsm")
+
+
+def test_prefiled_sort_counts_are_dropped_when_particles_move_elsewhere(Sim):
+    """On the single-GPU fast path pass B files the next step's counting-sort input (key / rank / per-cell count).  Anything
+    else that moves or replaces particles between two steps (the staged Update_Properties, Init_Fluid appending particles,
+    upload of a new state) must void it.  Reference: the same call sequence on the radix-sort path (params.reserved[2] = 1),
+    which never pre-files; the two differ only by summation order inside cells."""
+    g, kw = load_golden("lattice_24x10x12")
+    pos = g["positions"]
+    n = len(pos)
+    extra = (pos[:200] + np.float32(0.011)).astype(np.float32)
+
+    def run(mode):
+        s = Sim(capacity=n + 400, world=kw["world"], diagnostics=False)
+        p = s.get_params()
+        p.reserved[2] = mode
+        s._ck(s.lib.sphsm_set_params(s.h, p))
+        s.Init_Fluid(pos)
+        s.set_fields(fixed=g["init.fixed"], stim=g["init.stim"])
+        s.Animation(3)
+        for st in range(1, 8):  # one staged step: stage 7 moves the particles behind pass B's back
+            s.stage(st)
+        s.Animation(2)
+        s.cells_csr()           # consumes the pre-filed counts; the next step must count again
+        s.Animation(2)
+        s.Init_Fluid(extra)     # appends particles
+        s.Animation(2)
+        st8 = s.particles()
+        s.upload(st8)           # replaces the state (same values)
+        s.Animation(2)
+        return s.particles()
+
+    a, b = run(0), run(1)
+    assert len(a) == n + 200
+    for f in ("pos", "vel", "dens", "Vm"):
+        scale = max(1e-30, float(np.abs(b[f].astype(np.float64)).max()))
+        assert float(np.abs(a[f].astype(np.float64) - b[f].astype(np.float64)).max()) <= 2e-5 * scale, f

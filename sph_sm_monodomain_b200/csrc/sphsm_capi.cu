@@ -57,6 +57,14 @@ struct sphsm_handle {
     cudaEvent_t pev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // SPHSM_HOST_PROF: device-side brackets
     double pacc[4] = {0, 0, 0, 0};
     double meta_wait_us = 0.0;             // SPHSM_HOST_PROF: host time spent waiting for the plane boundaries
+    // NCCL mode: a rank-local step error (halo overflow, a particle crossing two planes) must not leave the peers waiting in
+    // a collective.  It is recorded, rides as one extra element on the NEXT step's moment allreduce, and every rank returns the
+    // error at the end of that step (so all ranks stop after the same step, at most one step late).
+    int local_error = 0;
+    std::string local_error_msg;
+    double *h_flag = nullptr;              // pinned: the summed error flag of the latest moment allreduce
+    cudaEvent_t ev_flag = nullptr;
+    bool flag_pending = false, peer_error = false, failed = false;
     bool reordered = false;                // slab step: the gather was queued before the plane boundaries reached the host
     bool split = false;                    // slab step: exchange 2 in flight on the side stream beside the interior planes
     Arrays cur{}, alt{};
@@ -343,6 +351,9 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_meta, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_flag, cudaEventDisableTiming));
+    CU(cudaMallocHost(&h->h_flag, sizeof(double)));
+    *h->h_flag = 0.0;
     CU(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&h->ev_in_ready, &h->ev_in_free, &h->ev_out_ready, &h->ev_out_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
@@ -401,6 +412,8 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_meta) cudaEventDestroy(h->ev_meta);
+    if (h->ev_flag) cudaEventDestroy(h->ev_flag);
+    if (h->h_flag) cudaFreeHost(h->h_flag);
     for (cudaEvent_t e : {h->ev_in_ready, h->ev_in_free, h->ev_out_ready, h->ev_out_done})
         if (e) cudaEventDestroy(e);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
@@ -1113,6 +1126,18 @@ static int moments_part(sphsm_handle *h) {
     else LAUNCH(k_moments<3>, B, 256, d, h->cur.P + off, h->cur.O + off, h->sm, h->partial);
     const int nacc = h->dp.quadratic ? 33 : 15;
     LAUNCH(k_sum_partials_par, nacc, 256, h->partial, B, nacc, h->totals);
+    if (h->comm_mode == 1) LAUNCH(k_store_double, 1, 1, h->totals + nacc, h->local_error ? 1.0 : 0.0);  // see local_error
+    return SPHSM_OK;
+}
+// the per-step moment allreduce (NCCL mode: + the error flag, copied back to the host for the next read-back to look at)
+static int moment_allreduce(sphsm_handle *h) {
+    const int nacc = h->dp.quadratic ? 33 : 15;
+    if (h->comm_mode != 1 || h->nranks == 1) return comm_allreduce(h, nacc);
+    int rc = comm_allreduce(h, nacc + 1);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h->h_flag, h->totals + nacc, sizeof(double), cudaMemcpyDeviceToHost, h->launch_stream));
+    CU(cudaEventRecord(h->ev_flag, h->launch_stream));
+    h->flag_pending = true;
     return SPHSM_OK;
 }
 
@@ -1128,7 +1153,7 @@ static int rest_moments(sphsm_handle *h) {
 static int sm_transform_fast(sphsm_handle *h) {
     int rc;
     if (h->rest_dirty && (rc = rest_moments(h)) != 0) return rc;
-    if ((rc = moments_part(h)) != 0 || (rc = comm_allreduce(h, h->dp.quadratic ? 33 : 15)) != 0) return rc;
+    if ((rc = moments_part(h)) != 0 || (rc = moment_allreduce(h)) != 0) return rc;
     LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
     return SPHSM_OK;
 }
@@ -1308,6 +1333,7 @@ extern "C" int sphsm_step(sphsm_handle *h, int nsteps) {
     if (!h || nsteps < 0) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
     if (h->comm_mode == 2) return fail(h, SPHSM_ERR_COMM, "a local group steps through sphsm_step_group");
+    if (h->failed) return fail(h, SPHSM_ERR_COMM, "the slab group stopped after a step error; re-upload the particle set and apply the slab again");
     CU(cudaEventRecord(h->ev_step0, h->stream));
     if (h->comm_mode == 1) {
         for (int s = 0; s < nsteps; s++) {
@@ -1606,8 +1632,19 @@ static int slab_meta_read(sphsm_handle *h) {
     CU(cudaEventSynchronize(h->ev_meta));  // (not the stream: work queued behind the read-back keeps running)
     if (tw != 0.0) h->meta_wait_us += now_us_early() - tw;
     const int *m = h->h_meta;
-    if (m[5]) return fail(h, SPHSM_ERR_COMM, "a particle crossed more than one cell plane in one step (or left the slab window)");
-    if (m[6]) return fail(h, SPHSM_ERR_COMM, "halo message overflow: raise params.reserved[0] (halo capacity)");
+    const char *what = m[5] ? "a particle crossed more than one cell plane in one step (or left the slab window)"
+                       : m[6] ? "halo message overflow: raise params.reserved[0] (halo capacity)" : nullptr;
+    const bool defer = h->comm_mode == 1 && h->nranks > 1 && h->slab_applied;  // inside an NCCL step: see local_error
+    if (what && !defer) return fail(h, SPHSM_ERR_COMM, what);
+    if (what && !h->local_error) {
+        h->local_error = 1;
+        h->local_error_msg = what;
+    }
+    if (defer && h->flag_pending) {
+        CU(cudaEventSynchronize(h->ev_flag));
+        h->flag_pending = false;
+        if (*h->h_flag != 0.0) h->peer_error = true;
+    }
     h->n = m[0];
     h->dp.n = m[0];
     h->dp.own_begin = m[1];
@@ -1644,6 +1681,8 @@ extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
     }
     h->grid_valid = false;
     h->slab_applied = true;
+    h->local_error = 0; h->peer_error = false; h->failed = false; h->flag_pending = false;
+    if (h->d_err) CU(cudaMemsetAsync(h->d_err, 0, 4 * sizeof(int), h->stream));
     return SPHSM_OK;
 }
 
@@ -1720,7 +1759,7 @@ static int nccl_exchange2(sphsm_handle *h, cudaStream_t st) {
 }
 
 // ---- the slab step as phases; every phase ends in the collective named by *coll ----------------------------------------
-enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE };
+enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE, COLL_ALLREDUCE_MOMENTS };
 static const int MG_PHASES = 6;
 
 static int mg_forked_allreduce(sphsm_handle *h);
@@ -1812,7 +1851,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             if (h->moments_forked || h->reordered) return SPHSM_OK;
             if (h->rest_dirty && (rc = rest_part3(h)) != 0) return rc;
             if ((rc = moments_part(h)) != 0) return rc;
-            *coll = COLL_ALLREDUCE; *count = h->dp.quadratic ? 33 : 15;
+            *coll = COLL_ALLREDUCE_MOMENTS; *count = h->dp.quadratic ? 33 : 15;
             return SPHSM_OK;
         case 4: {  // solve, gather + stage 2, pass A
             if (memcmp(&h->dp, &h->dp_uploaded, sizeof(DevParams)) != 0) {
@@ -1894,7 +1933,7 @@ static int mg_check(sphsm_handle *h) {
 // second half of the forked moment chain: allreduce + solve on the side stream, then the join event
 static int mg_forked_allreduce(sphsm_handle *h) {
     h->launch_stream = h->side_stream;
-    int rc = comm_allreduce(h, h->dp.quadratic ? 33 : 15);
+    int rc = moment_allreduce(h);
     if (!rc) rc = [&]() -> int { LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm); return SPHSM_OK; }();
     h->launch_stream = h->stream;
     if (rc) return rc;
@@ -1933,12 +1972,18 @@ static int mg_step_nccl(sphsm_handle *h) {
             if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[3], h->side_stream));
         }
         else if (coll == COLL_ALLREDUCE) rc = comm_allreduce(h, count);
+        else if (coll == COLL_ALLREDUCE_MOMENTS) rc = moment_allreduce(h);
         else if (coll == COLL_EXCH2) rc = nccl_exchange2(h, h->stream);
         if (rc) return rc;
         if (g_host_prof) {
             acc[ph][0] += t1 - t0;
             acc[ph][1] += now_us() - t1;
         }
+    }
+    if (h->peer_error) {  // some rank (maybe this one) failed in the previous step: every rank stops here
+        h->failed = true;
+        return fail(h, SPHSM_ERR_COMM, h->local_error ? h->local_error_msg.c_str()
+                                                      : "another rank of the slab group reported a step error (its sphsm_last_error has the cause)");
     }
     if (g_host_prof && h->pev[5] && h->split) {  // device-side durations of the three collectives (this serialises the steps)
         CU(cudaStreamSynchronize(h->stream));
@@ -1993,7 +2038,7 @@ extern "C" int sphsm_step_group(sphsm_handle **hs, int nranks, int nsteps) {
                     if (r > 0) CU(cudaMemcpy(hs[r]->msg_recv[0], hs[r - 1]->msg_send[1], bytes, cudaMemcpyDeviceToDevice));
                     if (r < nranks - 1) CU(cudaMemcpy(hs[r]->msg_recv[1], hs[r + 1]->msg_send[0], bytes, cudaMemcpyDeviceToDevice));
                 }
-            } else if (coll[0] == COLL_ALLREDUCE) {
+            } else if (coll[0] == COLL_ALLREDUCE || coll[0] == COLL_ALLREDUCE_MOMENTS) {
                 const int c = count[0];
                 std::fill(sum.begin(), sum.end(), 0.0);
                 for (int r = 0; r < nranks; r++) {

@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(256) k_mg_halo_vn(int n_left, int right_begin,
     VN[s] = V[s].w;
 }
 
+__global__ void k_store_double(double *dst, double v) { *dst = v; }
+
 // compact (id, xyz) of the owned slots for sphsm_download_owned
 __global__ void __launch_bounds__(256) k_mg_owned_out(int first, int count, Arrays a, int *__restrict__ ids, float *__restrict__ xyz) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -63,7 +63,10 @@ class Sim:
         p.strict = int(bool(strict))
         p.slab_axis = int(slab_axis)
         for k, v in overrides.items():
-            setattr(p, k, v)
+            if k == "halo_capacity":  # params.reserved[0]: particles per halo / migrant message (0 = default)
+                p.reserved[0] = int(v)
+            else:
+                setattr(p, k, v)
         self.h = C.c_void_p()
         _capi.check(self.lib, None, self.lib.sphsm_create(C.byref(p), C.byref(self.h)))
         self._stage_time = np.zeros(7)

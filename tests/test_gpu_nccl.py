@@ -32,3 +32,18 @@ def test_nccl_slabs_match_single_gpu(extra):
     assert res["mg_parity"] == "ok" and res["every_particle_owned_once"]
     if "--canonical" in extra:
         assert res["max_rel_dev_vs_single_gpu"] <= 2e-6
+
+
+def test_nccl_step_error_is_collective():
+    """A halo capacity too small for one cell plane: the rank that overflows records the error, it rides on the next step's
+    moment allreduce, and EVERY rank returns an error at the end of that step — nobody is left waiting in a collective."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tools", "mg_parity.py"), "--expect-overflow", "64"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["mg_error_path"] == "ok", res

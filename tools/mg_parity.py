@@ -27,6 +27,8 @@ ap.add_argument("--quadratic", action="store_true")
 ap.add_argument("--jitter", type=float, default=0.05)
 ap.add_argument("--tol", type=float, default=1e-5)
 ap.add_argument("--canonical", action="store_true", help="ascending-id order in every cell on all ranks (bit-level comparison)")
+ap.add_argument("--expect-overflow", type=int, default=0,
+                help="halo capacity too small on purpose: every rank must get SphsmError within a few steps, none may hang")
 a = ap.parse_args()
 rank, world_size, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -50,6 +52,36 @@ def make(**kw):
         s.flip_quadratic()
     return s
 
+
+if a.expect_overflow:
+    # error path: rank-local halo overflow -> reported by EVERY rank at the end of the following step, no rank left in a collective
+    from sph_sm_monodomain_b200 import SphsmError
+
+    sim = make(halo_capacity=a.expect_overflow)
+    ident = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0:
+        ident.copy_(torch.frombuffer(bytearray(Sim.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(ident, 0)
+    sim.comm_init(world_size, rank, bytes(ident.cpu().numpy().tobytes()))
+    sim.set_slab(*parts[rank])
+    failed_at, msg = -1, ""
+    for k in range(6):
+        try:
+            sim.Animation(1)
+            sim.sync()
+        except SphsmError as e:
+            failed_at, msg = k, str(e)
+            break
+    t = torch.tensor([failed_at], device=f"cuda:{local}")
+    got = [torch.zeros_like(t) for _ in range(world_size)]
+    dist.all_gather(got, t)
+    steps_failed = [int(x.item()) for x in got]
+    ok = all(s >= 0 for s in steps_failed) and len(set(steps_failed)) == 1
+    if rank == 0:
+        print(json.dumps({"mg_error_path": "ok" if ok else "FAIL", "ranks": world_size, "failed_at_step": steps_failed, "message_rank0": msg[:160]}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
 
 sim = make()
 if a.canonical:

@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 8m|1m|32m|<nx>x<ny>x<nz>]
 
-A "step" is one Animation() of the whole particle set: neighbour search (hash, radix sort, cell table, reorder),
+A "step" is one Animation() of the whole particle set: neighbour search (hash, counting sort = cell table, reorder),
 shape matching (moments, polar decomposition, goal positions), both neighbour passes, ionic model, integration.
 Default workload: BASELINE.json configs[3], the synthetic 8M-particle elongated lattice (512x125x125) with quadratic
 shape matching — the configuration the north_star's throughput target is quoted on; it fits one B200 and is
@@ -14,7 +14,8 @@ timed steps.
 One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events around exactly K steps, max over
 ranks); `e2e` = the same metric through the C-ABI with HOST buffers: every step uploads the per-particle stimulation
 array from pinned host memory (the per-step control input of this path) and downloads the positions (what the
-reference's viewer reads through Get_Paticles() every frame).  `roofline` is the dominant kernel (fused pass B) from
+reference's viewer reads through Get_Paticles() every frame), using the library's asynchronous I/O calls so that the
+copies of step k overlap the compute of step k+1; the timed region ends when the last result is in host memory.  `roofline` is the dominant kernel (fused pass B) from
 CUDA events on the handle's stream; `cpu_baseline` is the reference's own CPU step timed on this box (1 thread — the
 reference has no threading) on a bounded sample.
 """

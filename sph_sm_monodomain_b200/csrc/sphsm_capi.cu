@@ -20,6 +20,7 @@
 #include "sphsm_pass2.cuh"
 #include "sphsm_pass3.cuh"
 #include "sphsm_pass4.cuh"
+#include "sphsm_pass4w.cuh"
 #include "sphsm_pass5.cuh"
 #include "sphsm_sm.cuh"
 #include "sphsm_sort.cuh"
@@ -73,6 +74,7 @@ struct sphsm_handle {
     int sorted_buf = 0;  // which keys[] / vals[] hold the sorted result
     uint32_t *cell_count = nullptr, *tile_sums = nullptr;  // counting sort: per-cell counts (kept zero between steps), scan scratch
     bool bounds_ready = false;                             // grid_sort already produced the cell_start table
+    int *big_cells = nullptr, *big_count = nullptr;  // counting sort: worklist of cells too full for the one-thread in-cell sort
     bool counts_ready = false;  // pass B already filed keys / ranks / per-cell counts of the CURRENT positions (single-GPU fast step)
     int *cell_start = nullptr, *slot_of = nullptr;
     SmState *sm = nullptr;
@@ -373,6 +375,9 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaMalloc(&h->tile_state, (size_t)MAX_SORT_PASSES * h->max_tiles * RADIX * sizeof(uint32_t)));
     CU(cudaMalloc(&h->tile_counter, MAX_SORT_PASSES * sizeof(uint32_t)));
     CU(cudaMalloc(&h->slot_of, (size_t)cap * sizeof(int)));
+    CU(cudaMalloc(&h->big_cells, ((size_t)cap / BIG_CELL + 2) * sizeof(int)));
+    CU(cudaMalloc(&h->big_count, sizeof(int)));
+    CU(cudaMemset(h->big_count, 0, sizeof(int)));
     CU(cudaMalloc(&h->d_dp, sizeof(DevParams)));
     CU(cudaMalloc(&h->sm, sizeof(SmState)));
     CU(cudaMemset(h->sm, 0, sizeof(SmState)));
@@ -397,7 +402,7 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     free_arrays(h->cur, true);
     free_arrays(h->alt, false);
     for (int k = 0; k < 2; k++) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
-    cudaFree(h->cell_count); cudaFree(h->tile_sums);
+    cudaFree(h->cell_count); cudaFree(h->tile_sums); cudaFree(h->big_cells); cudaFree(h->big_count);
     cudaFree(h->ghist); cudaFree(h->tile_state); cudaFree(h->tile_counter); cudaFree(h->cell_start); cudaFree(h->slot_of);
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
     cudaFree(h->d_itmp);
@@ -1003,10 +1008,11 @@ static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt) {
     else LAUNCH(k_cell_count, cdiv(n, 256), 256, h->dp, h->cur.P, h->keys[0], h->keys[1], h->cell_count);
     if (gt) gt->end_group(KG_HASH);
     LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
-    LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles);
+    LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles, h->big_count);
     LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start);
     LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0]);
-    LAUNCH(k_cell_sort_ids, cdiv(h->dp.num_cells, 256), 256, h->cell_start, h->vals[0], h->cur.ID, h->dp.num_cells);
+    LAUNCH(k_cell_sort_ids, cdiv(h->dp.num_cells, 256), 256, h->cell_start, h->vals[0], h->cur.ID, h->dp.num_cells, h->big_cells, h->big_count);
+    LAUNCH(k_cell_sort_big, 64, 256, h->cell_start, h->vals[0], h->vals[1], h->cur.ID, h->big_cells, h->big_count);
     h->sorted_buf = 0;
     h->bounds_ready = true;
     if (gt) gt->end_group(KG_SORT);
@@ -1221,13 +1227,22 @@ static int run_stage(sphsm_handle *h, int stage) {
 }
 
 // the fast-path neighbour passes over the owned slot range (count = own_end - own_begin)
+// Small particle sets (the reference's own ~5k-particle inputs) take one warp per particle (sphsm_pass4w.cuh).  The choice
+// follows the GLOBAL particle count, so that a slab rank and the single-GPU run of the same set use the same kernels (the
+// bit-level slab parity depends on identical summation order).  SPHSM_WARP_PATH=0 disables it.
+static bool warp_path(const sphsm_handle *h) {
+    static const bool off = getenv("SPHSM_WARP_PATH") && atoi(getenv("SPHSM_WARP_PATH")) == 0;
+    if (off || g_pass_gen < 4) return false;
+    return (h->dp.slab_on ? h->n_global : h->n) <= WARP_PATH_MAX;
+}
 // slots [begin, end) minus the hole [hole_b, hole_e) (generation-4 kernels only)
 static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0) {
     const int count = end - begin - (hole_e - hole_b);
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
-    if (g_pass_gen == 5) LAUNCH(k_pass_a5, cdiv(cdiv(count, 2), PT5), PT5, d, h->d_dp, h->cur, h->cell_start, count);
+    if (warp_path(h)) LAUNCH(k_pass_a4w, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->cell_start, count);
+    else if (g_pass_gen == 5) LAUNCH(k_pass_a5, cdiv(cdiv(count, 2), PT5), PT5, d, h->d_dp, h->cur, h->cell_start, count);
     else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start);
     else if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
     else LAUNCH(k_pass_a3, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
@@ -1239,7 +1254,10 @@ static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hol
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
-    if (g_pass_gen == 4 || g_pass_gen == 5) {
+    if (warp_path(h)) {
+        if (diag) LAUNCH(k_pass_b4w<true>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count);
+        else LAUNCH(k_pass_b4w<false>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count);
+    } else if (g_pass_gen == 4 || g_pass_gen == 5) {
         if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt);
         else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt);
     } else if (g_pass_gen == 2) {

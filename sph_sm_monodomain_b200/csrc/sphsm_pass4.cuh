@@ -233,6 +233,36 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
     if (z >= p.world[2]) { vz *= p.wall_hit; z = __fsub_rn(p.world[2], 0.0001f); }
 }
 
+// pass B's per-particle tail, shared by the thread-per-particle and the warp-per-particle kernels: acceleration, Inter_Vm
+// (cpp:568-571), Update_Properties (cpp:602-649), and — when cell_count is given — the next step's counting-sort input.
+// e4 = (Vm, Iion, w, stim) AFTER the ionic model; L = the SPH Laplacian sum of Vm.
+template <bool DIAG>
+__device__ __forceinline__ void pass_b_finish(const DevParams &p, const Arrays &a, float4 *__restrict__ Pout, const int i, const float4 pi,
+                                              const float4 vi, float4 e4, float ax, float ay, float az, const float L, const float inv_mass,
+                                              uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count) {
+    float4 v4 = a.VEL[i];
+    const float inv_dens = rcp_ftz(v4.w);
+    ax *= inv_dens;  // cpp:568
+    ay *= inv_dens;
+    az *= inv_dens;
+    // cpp:571: Inter_Vm += (sigma/(Beta*Cm))*Inter_Vm - ((Iion - stim*dt/mass)/Cm)   (the += form, Q9)
+    const float dtm = p.dt * inv_mass;
+    const float ivm = SPHSM_FAST_ODE ? L + (p.diff_coef * L - (e4.y - e4.w * dtm) / p.Cm) : L + (p.diff_coef * L - (e4.y - (e4.w * p.dt) / pi.w) / p.Cm);
+    if (DIAG) a.ACC[i] = make_float4(ax, ay, az, ivm);
+    const bool fixed = __float_as_int(a.O[i].w) != 0;
+    float x = pi.x, y = pi.y, z = pi.z;
+    integrate_fast(p, fixed, dtm, vi.x, vi.y, vi.z, ax, ay, az, ivm, pi.w, x, y, z, v4.x, v4.y, v4.z, e4.x);
+    Pout[i] = make_float4(x, y, z, pi.w);
+    a.VEL[i] = v4;
+    a.E[i] = e4;
+    if (cell_count) {
+        int ca, cb, cc;
+        const uint32_t key = cell_coords(p, x, y, z, ca, cb, cc) ? (uint32_t)cell_key(p, ca, cb, cc) : (uint32_t)p.num_cells;
+        next_keys[i] = key;
+        next_rank[i] = atomicAdd(&cell_count[key], 1u);
+    }
+}
+
 #ifndef SPHSM_B_STEP
 #define SPHSM_B_STEP 2  // candidates per unchecked iteration of pass B phase 1 (2 or 4; 4 needs 72 registers and measured 686 us against 678)
 #endif
@@ -342,27 +372,7 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
                 lo = lbase;
             });
     }
-    L += L1;
-    float4 v4 = a.VEL[i];
-    const float inv_dens = rcp_ftz(v4.w);
-    ax *= inv_dens;  // cpp:568
-    ay *= inv_dens;
-    az *= inv_dens;
-    // cpp:571: Inter_Vm += (sigma/(Beta*Cm))*Inter_Vm - ((Iion - stim*dt/mass)/Cm)   (the += form, Q9)
-    const float dtm = p.dt * inv_mass;
-    const float ivm = SPHSM_FAST_ODE ? L + (p.diff_coef * L - (e4.y - e4.w * dtm) / p.Cm) : L + (p.diff_coef * L - (e4.y - (e4.w * p.dt) / pi.w) / p.Cm);
-    if (DIAG) a.ACC[i] = make_float4(ax, ay, az, ivm);
-    const bool fixed = __float_as_int(a.O[i].w) != 0;
-    float x = pi.x, y = pi.y, z = pi.z;
-    integrate_fast(p, fixed, dtm, vi.x, vi.y, vi.z, ax, ay, az, ivm, pi.w, x, y, z, v4.x, v4.y, v4.z, e4.x);
-    Pout[i] = make_float4(x, y, z, pi.w);
-    a.VEL[i] = v4;
-    a.E[i] = e4;
-    if (cell_count) {
-        const uint32_t key = cell_coords(p, x, y, z, ca, cb, cc) ? (uint32_t)cell_key(p, ca, cb, cc) : (uint32_t)p.num_cells;
-        next_keys[i] = key;
-        next_rank[i] = atomicAdd(&cell_count[key], 1u);
-    }
+    pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, ax, ay, az, L + L1, inv_mass, next_keys, next_rank, cell_count);
 }
 
 }  // namespace sphsm

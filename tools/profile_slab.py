@@ -21,7 +21,7 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 a = ap.parse_args()
 wl = bench.parse_workload(a.workload)
-pos, world, fixed, stim = bench.make_lattice(wl["dims"])
+pos, world, fixed, stim = bench.workload_inputs(wl)
 axis = slabs.slab_axis_for(world)
 npl = slabs.num_planes(world, axis)
 parts = slabs.partition_planes(slabs.plane_histogram(pos, axis, npl), a.ranks)

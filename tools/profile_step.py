@@ -16,7 +16,7 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 a = ap.parse_args()
 wl = bench.parse_workload(a.workload)
-pos, world, fixed, stim = bench.make_lattice(wl["dims"])
+pos, world, fixed, stim = bench.workload_inputs(wl)
 sim = Sim(capacity=len(pos), world=world, diagnostics=False)
 sim.Init_Fluid(pos)
 sim.set_masks(fixed, stim)

@@ -74,6 +74,14 @@ struct sphsm_handle {
     int sorted_buf = 0;  // which keys[] / vals[] hold the sorted result
     uint32_t *cell_count = nullptr, *tile_sums = nullptr;  // counting sort: per-cell counts (kept zero between steps), scan scratch
     bool bounds_ready = false;                             // grid_sort already produced the cell_start table
+    // CUDA graphs for small single-GPU steps (launch-latency bound): see graph_step
+    bool dry_run = false;  // replaying a captured step: the host-side state transitions run, launches and stream calls do not
+    struct StepGraph {
+        std::string sig;
+        cudaGraphExec_t exec;
+    };
+    std::vector<StepGraph> graphs;
+    std::vector<std::string> seen_sigs;
     int *big_cells = nullptr, *big_count = nullptr;  // counting sort: worklist of cells too full for the one-thread in-cell sort
     bool counts_ready = false;  // pass B already filed keys / ranks / per-cell counts of the CURRENT positions (single-GPU fast step)
     int *cell_start = nullptr, *slot_of = nullptr;
@@ -142,7 +150,7 @@ static const bool g_sync_debug = getenv("SPHSM_SYNC_DEBUG") != nullptr;
 static const int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 4;
 #define LAUNCH(kern, grid, block, ...)                                                                  \
     do {                                                                                                \
-        kern<<<(grid), (block), 0, h->launch_stream>>>(__VA_ARGS__);                                    \
+        if (!h->dry_run) kern<<<(grid), (block), 0, h->launch_stream>>>(__VA_ARGS__);                   \
         h->launches++;                                                                                  \
         if (g_sync_debug) {                                                                             \
             cudaError_t e_ = cudaStreamSynchronize(h->launch_stream);                                   \
@@ -416,6 +424,8 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     if (h->ev_step1) cudaEventDestroy(h->ev_step1);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (auto &gx : h->graphs) cudaGraphExecDestroy(gx.exec);
+    h->graphs.clear();
     if (h->ev_meta) cudaEventDestroy(h->ev_meta);
     if (h->ev_flag) cudaEventDestroy(h->ev_flag);
     if (h->h_flag) cudaFreeHost(h->h_flag);
@@ -1288,16 +1298,18 @@ static int fused_step(sphsm_handle *h) {
         // and rejoin before the gather applies the transform (kept in line while the per-group timers are on)
         const bool fork = !h->rest_dirty && !h->profiling;
         if (fork) {
-            CU(cudaEventRecord(h->ev_fork, h->stream));
-            CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            if (!h->dry_run) {
+                CU(cudaEventRecord(h->ev_fork, h->stream));
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            }
             h->launch_stream = h->side_stream;
             rc = sm_transform_fast(h);
             h->launch_stream = h->stream;
             if (rc) return rc;
-            CU(cudaEventRecord(h->ev_join, h->side_stream));
+            if (!h->dry_run) CU(cudaEventRecord(h->ev_join, h->side_stream));
         }
         if ((rc = grid_sort(h, &gt)) != 0) return rc;
-        if (fork) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        if (fork && !h->dry_run) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         else if ((rc = sm_transform_fast(h)) != 0) return rc;
         gt.end_group(KG_MOMENTS);
         if ((rc = grid_finish(h, &gt, diag ? 2 : 1)) != 0) return rc;
@@ -1347,6 +1359,75 @@ static int timed_staged_step(sphsm_handle *h) {
 
 static int mg_step_nccl(sphsm_handle *h);  // the slab step (below)
 
+// Small single-GPU steps are launch-latency bound (13 dependent launches of 3-5 us for a few microseconds of work each at the
+// reference's own ~5k particles), so the fast step is captured into a CUDA graph and replayed.  A step's launch sequence and
+// arguments are a function of the handle's state only (no data-dependent host decisions on one GPU): that state — buffer
+// pointers of both ping-pong sets, the device parameter block, the sort / counting flags — is the graph's signature.  A
+// signature seen for the second time is captured (the ping-pong gives two signatures in steady state); on a hit the host
+// runs the step's bookkeeping with launches suppressed (dry_run) and launches the graph.  Any mutator that changes what a
+// step would launch changes the signature, so a stale graph cannot be picked.  params.reserved[4] = 1 turns graphs off.
+static const int GRAPH_MAX_N = 1 << 18;
+static bool graph_eligible(const sphsm_handle *h) {
+    return h->comm_mode == 0 && !h->prm.strict && !h->profiling && !h->stage_timing && !g_sync_debug && h->prm.reserved[4] != 1 && h->n > 1 &&
+           h->n <= GRAPH_MAX_N && !h->rest_dirty && memcmp(&h->dp, &h->dp_uploaded, sizeof(DevParams)) == 0 && !getenv("SPHSM_NO_GRAPH");
+}
+static std::string step_signature(const sphsm_handle *h) {
+    std::string sig;
+    auto put = [&](const void *ptr, size_t bytes) { sig.append(reinterpret_cast<const char *>(ptr), bytes); };
+    put(&h->cur, sizeof(Arrays));
+    put(&h->alt, sizeof(Arrays));
+    put(&h->dp, sizeof(DevParams));
+    put(&h->prm, sizeof(sphsm_params));
+    const void *ptrs[] = {h->cell_start, h->cell_count, h->tile_sums, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->big_cells, h->big_count,
+                          h->sm, h->partial, h->totals, h->d_dp, h->ghist, h->tile_state, h->tile_counter, h->scratch};
+    put(ptrs, sizeof(ptrs));
+    const int flags[] = {h->counts_ready, h->bounds_ready, h->sorted_buf, g_pass_gen, h->red_blocks, h->sort_passes, (int)h->grid_valid};
+    put(flags, sizeof(flags));
+    return sig;
+}
+static int graph_step(sphsm_handle *h) {
+    if (!graph_eligible(h)) return fused_step<false>(h);
+    const std::string sig = step_signature(h);
+    for (auto &gx : h->graphs) {
+        if (gx.sig == sig) {
+            h->dry_run = true;
+            const int rc = fused_step<false>(h);
+            h->dry_run = false;
+            if (rc) return rc;
+            CU(cudaGraphLaunch(gx.exec, h->stream));
+            return SPHSM_OK;
+        }
+    }
+    bool seen = false;
+    for (auto &x : h->seen_sigs) seen = seen || x == sig;
+    if (!seen) {
+        if (h->seen_sigs.size() >= 16) h->seen_sigs.clear();
+        h->seen_sigs.push_back(sig);
+        return fused_step<false>(h);
+    }
+    // second sighting: capture this step (it executes when the graph is launched below)
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+    const int rc = fused_step<false>(h);
+    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    if (rc || ce != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc ? rc : fail(h, SPHSM_ERR_CUDA, "CUDA graph capture of the step failed");
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail(h, SPHSM_ERR_CUDA, "cudaGraphInstantiate failed");
+    if (h->graphs.size() >= 8) {
+        for (auto &gx : h->graphs) cudaGraphExecDestroy(gx.exec);
+        h->graphs.clear();
+    }
+    h->graphs.push_back({sig, exec});
+    CU(cudaGraphLaunch(exec, h->stream));
+    return SPHSM_OK;
+}
+
 extern "C" int sphsm_step(sphsm_handle *h, int nsteps) {
     if (!h || nsteps < 0) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
@@ -1364,7 +1445,7 @@ extern "C" int sphsm_step(sphsm_handle *h, int nsteps) {
     for (int s = 0; s < nsteps; s++) {
         int rc;
         if (h->stage_timing) rc = h->prm.strict ? timed_staged_step<true>(h) : timed_staged_step<false>(h);
-        else rc = h->prm.strict ? fused_step<true>(h) : fused_step<false>(h);
+        else rc = h->prm.strict ? fused_step<true>(h) : graph_step(h);
         if (rc) return rc;
         h->total_steps++;
     }

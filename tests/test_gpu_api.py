@@ -310,3 +310,50 @@ def test_prefiled_sort_counts_are_dropped_when_particles_move_elsewhere(Sim):
     for f in ("pos", "vel", "dens", "Vm"):
         scale = max(1e-30, float(np.abs(b[f].astype(np.float64)).max()))
         assert float(np.abs(a[f].astype(np.float64) - b[f].astype(np.float64)).max()) <= 2e-5 * scale, f
+
+
+@pytest.mark.parametrize("name", ["lattice_24x10x12", "cfg2_5211_wave"])
+def test_graph_replay_is_bit_identical(Sim, name):
+    """Small single-GPU steps are captured into CUDA graphs and replayed (params.reserved[4] = 1 turns that off).  A replayed
+    step launches exactly the kernels of the eager step, so the state must agree BIT FOR BIT — also across everything that
+    changes what a step launches or reads: mask updates (rest-state sums become dirty), parameter changes (new device parameter
+    block), appended particles, staged calls and downloads in between."""
+    g, kw = load_golden(name)
+    pos = g["positions"]
+    extra = (pos[:50] + np.float32(0.013)).astype(np.float32)
+    if "capacity" in kw:
+        kw = dict(kw, capacity=kw["capacity"] + 100)
+    rng = np.random.default_rng(11)
+    stim2 = np.where(rng.random(len(pos)) < 0.3, np.float32(300), np.float32(0)).astype(np.float32)
+    fixed2 = (rng.random(len(pos)) < 0.03).astype(np.uint8)
+
+    def run(graphs_off):
+        s = Sim(diagnostics=False, **kw)
+        p = s.get_params()
+        p.reserved[4] = 1 if graphs_off else 0
+        s._ck(s.lib.sphsm_set_params(s.h, p))
+        s.Init_Fluid(pos)
+        s.set_fields(fixed=g["init.fixed"], stim=g["init.stim"])
+        snaps = []
+        s.Animation(12)
+        snaps.append(s.positions())
+        s.set_masks(None, stim2)       # stimulation only: graphs stay valid
+        s.Animation(7)
+        s.set_masks(fixed2, None)      # fixed flags: rest-state sums are recomputed by one eager step
+        s.Animation(7)
+        snaps.append(s.positions())
+        s.add_viscosity(0.5)           # new parameter block
+        s.Animation(6)
+        s.stage("Find_neighbors")      # a staged call between steps
+        s.cells_csr()
+        s.Animation(5)
+        s.Init_Fluid(extra)            # more particles
+        s.Animation(9)
+        snaps.append(s.positions())
+        return snaps, s.particles()
+
+    (sa, a), (sb, b) = run(True), run(False)
+    for x, y in zip(sa, sb):
+        assert bits_equal(x, y)
+    for f in ("pos", "vel", "dens", "pres", "Vm", "Iion", "w", "stim", "fixed", "orig", "mass"):
+        assert bits_equal(a[f], b[f]), f

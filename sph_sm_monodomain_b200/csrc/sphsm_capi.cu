@@ -1309,8 +1309,9 @@ static int fused_step(sphsm_handle *h) {
             if (!h->dry_run) CU(cudaEventRecord(h->ev_join, h->side_stream));
         }
         if ((rc = grid_sort(h, &gt)) != 0) return rc;
-        if (fork && !h->dry_run) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        else if ((rc = sm_transform_fast(h)) != 0) return rc;
+        if (fork) {
+            if (!h->dry_run) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        } else if ((rc = sm_transform_fast(h)) != 0) return rc;
         gt.end_group(KG_MOMENTS);
         if ((rc = grid_finish(h, &gt, diag ? 2 : 1)) != 0) return rc;
     } else {
@@ -1360,13 +1361,13 @@ static int timed_staged_step(sphsm_handle *h) {
 static int mg_step_nccl(sphsm_handle *h);  // the slab step (below)
 
 // Small single-GPU steps are launch-latency bound (13 dependent launches of 3-5 us for a few microseconds of work each at the
-// reference's own ~5k particles), so the fast step is captured into a CUDA graph and replayed.  A step's launch sequence and
+// reference's own ~5k particles; still 2-4 % of the step at 1-2M), so the fast step is captured into a CUDA graph and replayed.  A step's launch sequence and
 // arguments are a function of the handle's state only (no data-dependent host decisions on one GPU): that state — buffer
 // pointers of both ping-pong sets, the device parameter block, the sort / counting flags — is the graph's signature.  A
 // signature seen for the second time is captured (the ping-pong gives two signatures in steady state); on a hit the host
 // runs the step's bookkeeping with launches suppressed (dry_run) and launches the graph.  Any mutator that changes what a
 // step would launch changes the signature, so a stale graph cannot be picked.  params.reserved[4] = 1 turns graphs off.
-static const int GRAPH_MAX_N = 1 << 18;
+static const int GRAPH_MAX_N = getenv("SPHSM_GRAPH_MAX_N") ? atoi(getenv("SPHSM_GRAPH_MAX_N")) : (1 << 22);  // measured: -22 % at 5k, -3.6 % at 1M, -2.2 % at 2M particles
 static bool graph_eligible(const sphsm_handle *h) {
     return h->comm_mode == 0 && !h->prm.strict && !h->profiling && !h->stage_timing && !g_sync_debug && h->prm.reserved[4] != 1 && h->n > 1 &&
            h->n <= GRAPH_MAX_N && !h->rest_dirty && memcmp(&h->dp, &h->dp_uploaded, sizeof(DevParams)) == 0 && !getenv("SPHSM_NO_GRAPH");

@@ -1369,8 +1369,9 @@ static int mg_step_nccl(sphsm_handle *h);  // the slab step (below)
 // step would launch changes the signature, so a stale graph cannot be picked.  params.reserved[4] = 1 turns graphs off.
 static const int GRAPH_MAX_N = getenv("SPHSM_GRAPH_MAX_N") ? atoi(getenv("SPHSM_GRAPH_MAX_N")) : (1 << 22);  // measured: -22 % at 5k, -3.6 % at 1M, -2.2 % at 2M particles
 static bool graph_eligible(const sphsm_handle *h) {
-    return h->comm_mode == 0 && !h->prm.strict && !h->profiling && !h->stage_timing && !g_sync_debug && h->prm.reserved[4] != 1 && h->n > 1 &&
-           h->n <= GRAPH_MAX_N && !h->rest_dirty && memcmp(&h->dp, &h->dp_uploaded, sizeof(DevParams)) == 0 && !getenv("SPHSM_NO_GRAPH");
+    static const bool env_off = getenv("SPHSM_NO_GRAPH") != nullptr;
+    return !env_off && h->comm_mode == 0 && !h->prm.strict && !h->profiling && !h->stage_timing && !g_sync_debug && h->prm.reserved[4] != 1 && h->n > 1 &&
+           h->n <= GRAPH_MAX_N && !h->rest_dirty && memcmp(&h->dp, &h->dp_uploaded, sizeof(DevParams)) == 0;
 }
 static std::string step_signature(const sphsm_handle *h) {
     std::string sig;

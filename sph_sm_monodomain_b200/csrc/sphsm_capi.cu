@@ -1036,9 +1036,11 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
     h->bounds_ready = false;
     const int passes = h->sort_passes;
     const int tiles = cdiv(n, SORT_TILE);
-    CU(cudaMemsetAsync(h->ghist, 0, MAX_SORT_PASSES * RADIX * sizeof(uint32_t), h->stream));
-    CU(cudaMemsetAsync(h->tile_state, 0, (size_t)passes * tiles * RADIX * sizeof(uint32_t), h->stream));
-    CU(cudaMemsetAsync(h->tile_counter, 0, MAX_SORT_PASSES * sizeof(uint32_t), h->stream));
+    if (!h->dry_run) {  // (a replayed graph carries its own copies of these nodes)
+        CU(cudaMemsetAsync(h->ghist, 0, MAX_SORT_PASSES * RADIX * sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(h->tile_state, 0, (size_t)passes * tiles * RADIX * sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(h->tile_counter, 0, MAX_SORT_PASSES * sizeof(uint32_t), h->stream));
+    }
     LAUNCH(k_hash, std::min(cdiv(n, 256), 8 * 148), 256, h->dp, h->cur.P, h->keys[0], h->ghist, passes);
     if (gt) gt->end_group(KG_HASH);
     int src = 0;

@@ -1241,11 +1241,16 @@ static int run_stage(sphsm_handle *h, int stage) {
 // the fast-path neighbour passes over the owned slot range (count = own_end - own_begin)
 // Small particle sets (the reference's own ~5k-particle inputs) take one warp per particle (sphsm_pass4w.cuh).  The choice
 // follows the GLOBAL particle count, so that a slab rank and the single-GPU run of the same set use the same kernels (the
-// bit-level slab parity depends on identical summation order).  SPHSM_WARP_PATH=0 disables it.
+// bit-level slab parity depends on identical summation order).  SPHSM_WARP_PATH=0 disables it, SPHSM_WARP_PATH_MAX moves the limit.
+// The limit is a particle count because that is all the host knows; what actually decides is candidates per stencil row:
+// measured with the limit lifted, a 64k LATTICE (3-6 candidates per row, most lanes idle) runs pass A / B in 56 / 108 us on
+// this path against 16 / 21 us on the thread path, while the reference's meshes (45 per row) gain 10x.  Below the limit both
+// are a few tens of microseconds; a density-aware choice (mean cell occupancy from the cell table) is left for later.
 static bool warp_path(const sphsm_handle *h) {
     static const bool off = getenv("SPHSM_WARP_PATH") && atoi(getenv("SPHSM_WARP_PATH")) == 0;
     if (off || g_pass_gen < 4) return false;
-    return (h->dp.slab_on ? h->n_global : h->n) <= WARP_PATH_MAX;
+    static const int limit = getenv("SPHSM_WARP_PATH_MAX") ? atoi(getenv("SPHSM_WARP_PATH_MAX")) : WARP_PATH_MAX;
+    return (h->dp.slab_on ? h->n_global : h->n) <= limit;
 }
 // slots [begin, end) minus the hole [hole_b, hole_e) (generation-4 kernels only)
 static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0) {

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "sphsm_comm.cuh"
@@ -82,6 +83,7 @@ struct sphsm_handle {
     };
     std::vector<StepGraph> graphs;
     std::vector<std::string> seen_sigs;
+    std::unordered_set<long long> host_cells;  // cells occupied by the positions the host handed in (small sets only): see warp_path
     int *big_cells = nullptr, *big_count = nullptr;  // counting sort: worklist of cells too full for the one-thread in-cell sort
     bool counts_ready = false;  // pass B already filed keys / ranks / per-cell counts of the CURRENT positions (single-GPU fast step)
     int *cell_start = nullptr, *slot_of = nullptr;
@@ -664,6 +666,21 @@ static void state_changed(sphsm_handle *h, bool rest) {
     }
 }
 
+// Host-side estimate of the mean cell occupancy of a small particle set, from the positions as the caller hands them in
+// (Init_Fluid / upload): what decides between the thread-per-particle and the warp-per-particle passes is candidates per
+// stencil row, i.e. particles per occupied cell, and the host never sees the cell table.  Only tracked up to the warp-path limit.
+static void note_host_positions(sphsm_handle *h, const float *x, size_t stride_floats, int count, bool reset) {
+    if (reset) h->host_cells.clear();
+    if (h->n + count > 4 * WARP_PATH_MAX || (int)h->host_cells.size() > 4 * WARP_PATH_MAX) return;
+    const float cs = h->prm.kernel_h;
+    for (int k = 0; k < count; k++) {
+        const float *q = x + (size_t)k * stride_floats;
+        if (!(fabsf(q[0]) < 1e9f && fabsf(q[1]) < 1e9f && fabsf(q[2]) < 1e9f)) continue;  // NaN / absurd: no cell
+        const long long cx = (long long)(q[0] / cs), cy = (long long)(q[1] / cs), cz = (long long)(q[2] / cs);
+        h->host_cells.insert((cx & 0x1fffff) | ((cy & 0x1fffff) << 21) | ((cz & 0x1fffff) << 42));
+    }
+}
+
 extern "C" int sphsm_init_fluid(sphsm_handle *h, const float *xyz, int n) {
     if (!h || (!xyz && n > 0) || n < 0) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
@@ -675,6 +692,7 @@ extern "C" int sphsm_init_fluid(sphsm_handle *h, const float *xyz, int n) {
     LAUNCH(k_init_particles, cdiv(take, 256), 256, h->n, take, h->d_tmp, h->cur, h->prm.particle_mass, h->prm.stand_density);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));  // xyz may be pageable / freed by the caller
+    note_host_positions(h, xyz, 3, take, h->n == 0);
     set_n(h, h->n + take);
     state_changed(h, true);
     return SPHSM_OK;
@@ -690,6 +708,10 @@ extern "C" int sphsm_upload_aos(sphsm_handle *h, const void *particles, int n, i
     if (n > 0) LAUNCH(k_aos_to_soa, cdiv(n, 256), 256, 0, n, h->d_aos, stride, h->cur);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
+    if (stride % 4 == 0) {
+        h->n = 0;
+        note_host_positions(h, reinterpret_cast<const float *>(static_cast<const uint8_t *>(particles) + OFF_POS), (size_t)stride / 4, n, true);
+    } else h->host_cells.clear();
     set_n(h, n);
     state_changed(h, true);
     return SPHSM_OK;
@@ -1244,13 +1266,16 @@ static int run_stage(sphsm_handle *h, int stage) {
 // bit-level slab parity depends on identical summation order).  SPHSM_WARP_PATH=0 disables it, SPHSM_WARP_PATH_MAX moves the limit.
 // The limit is a particle count because that is all the host knows; what actually decides is candidates per stencil row:
 // measured with the limit lifted, a 64k LATTICE (3-6 candidates per row, most lanes idle) runs pass A / B in 56 / 108 us on
-// this path against 16 / 21 us on the thread path, while the reference's meshes (45 per row) gain 10x.  Below the limit both
-// are a few tens of microseconds; a density-aware choice (mean cell occupancy from the cell table) is left for later.
+// this path against 16 / 21 us on the thread path, while the reference's meshes (45 per row) gain 10x.  Hence the second
+// condition: at least 3 particles per occupied cell, estimated on the host from the positions as they were handed in
+// (note_host_positions; the reference's sets have 4.9-5.1, lattices of spacing 0.9 h have 1.4).
 static bool warp_path(const sphsm_handle *h) {
     static const bool off = getenv("SPHSM_WARP_PATH") && atoi(getenv("SPHSM_WARP_PATH")) == 0;
     if (off || g_pass_gen < 4) return false;
     static const int limit = getenv("SPHSM_WARP_PATH_MAX") ? atoi(getenv("SPHSM_WARP_PATH_MAX")) : WARP_PATH_MAX;
-    return (h->dp.slab_on ? h->n_global : h->n) <= limit;
+    const int n = h->dp.slab_on ? h->n_global : h->n;
+    if (n > limit || h->host_cells.empty()) return false;
+    return (double)n >= 3.0 * (double)h->host_cells.size();  // >= 3 particles per occupied cell: rows long enough for a warp
 }
 // slots [begin, end) minus the hole [hole_b, hole_e) (generation-4 kernels only)
 static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0) {

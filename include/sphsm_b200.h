@@ -87,7 +87,15 @@ typedef struct {
                                0: the production path. */
     int32_t slab_axis;      /* multi-GPU: axis (0,1,2) the domain is cut along; also the slowest-varying axis of
                                the internal cell key. -1: single-GPU reference key order (x fastest). */
-    int32_t reserved[8];
+    int32_t reserved[8];    /* tuning / validation switches, 0 = default everywhere:
+                               [0] multi-GPU: particles per halo / migrant message (default: 2.5 x the mean cell-plane
+                                   population at capacity + 4096)
+                               [1] 1: canonical in-cell order (ascending original index) in EVERY cell of a slab rank, not
+                                   only next to the slab faces (bit-level comparison against the single-GPU run)
+                               [2] neighbour-grid sort: 1 = LSD radix sort, 2 = counting sort (default: by grid size)
+                               [3] unused
+                               [4] 1: no CUDA-graph replay of small single-GPU steps
+                               [5..7] unused */
 } sphsm_params;
 
 typedef struct sphsm_handle sphsm_handle;

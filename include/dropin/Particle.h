@@ -4,6 +4,7 @@
 #ifndef SPHSM_DROPIN_PARTICLE_H
 #define SPHSM_DROPIN_PARTICLE_H
 
+#include <cstddef>
 #include <vector>
 
 #include "m3Vector.h"
@@ -34,6 +35,14 @@ public:
     m3Real getDisplacement() { return (mOriginalPos - pos).magnitude(); }
 };
 static_assert(sizeof(Particle) == 132, "Particle must keep the reference's 132-byte layout");
+// the byte offsets the device-side AoS <-> SoA kernels use (sphsm_capi.cu: OFF_*)
+static_assert(offsetof(Particle, vel) == 12 && offsetof(Particle, predicted_vel) == 24 && offsetof(Particle, inter_vel) == 36 &&
+                  offsetof(Particle, corrected_vel) == 48 && offsetof(Particle, acc) == 60 && offsetof(Particle, mass) == 72 &&
+                  offsetof(Particle, mOriginalPos) == 76 && offsetof(Particle, mGoalPos) == 88 && offsetof(Particle, mFixed) == 100 &&
+                  offsetof(Particle, dens) == 104 && offsetof(Particle, pres) == 108 && offsetof(Particle, Vm) == 112 &&
+                  offsetof(Particle, Inter_Vm) == 116 && offsetof(Particle, Iion) == 120 && offsetof(Particle, stim) == 124 &&
+                  offsetof(Particle, w) == 128,
+              "Particle field offsets differ from the image sphsm_upload_aos / sphsm_download_aos exchange");
 
 class Cell {
 public:

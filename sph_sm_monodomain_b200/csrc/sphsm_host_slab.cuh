@@ -1,0 +1,571 @@
+// sphsm_host_slab.cuh — the multi-GPU slab layer: NCCL loader, communicator setup, slab bookkeeping, exchanges, the phase program of the slab step (NCCL and virtual ranks)
+// Host code of libsphsm_b200.so, textually included by sphsm_capi.cu (one translation unit: the handle, the LAUNCH / CU macros and
+// the static helpers defined there are in scope).
+#pragma once
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU slab layer, host side.  NCCL is resolved at run time (dlopen), so single-GPU hosts need no NCCL.
+typedef struct { char internal[128]; } nccl_unique_id;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(nccl_unique_id *) = nullptr;
+    int (*CommInitRank)(void **, int, nccl_unique_id, int) = nullptr;
+    int (*CommSplit)(void *, int, int, void **, void *) = nullptr;  // optional (NCCL >= 2.18)
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+enum { NCCL_CHAR = 0, NCCL_FLOAT = 7, NCCL_DOUBLE = 8, NCCL_SUM = 0 };  // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+static int load_nccl(sphsm_handle *h) {
+    if (g_nccl.lib) return SPHSM_OK;
+    const char *names[] = {getenv("SPHSM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *lib = nullptr;
+    for (const char *nm : names)
+        if (nm && (lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break;
+    if (!lib) return fail(h, SPHSM_ERR_COMM, "libnccl.so.2 not found (set SPHSM_NCCL_LIB)");
+    bool ok = true;
+    auto sym = [&](const char *nm) { void *f = dlsym(lib, nm); if (!f) ok = false; return f; };
+    g_nccl.GetUniqueId = (int (*)(nccl_unique_id *))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, nccl_unique_id, int))sym("ncclCommInitRank");
+    g_nccl.CommSplit = (int (*)(void *, int, int, void **, void *))dlsym(lib, "ncclCommSplit");
+    g_nccl.CommDestroy = (int (*)(void *))sym("ncclCommDestroy");
+    g_nccl.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))sym("ncclSend");
+    g_nccl.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))sym("ncclRecv");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))sym("ncclAllReduce");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+    if (!ok) return fail(h, SPHSM_ERR_COMM, "libnccl is missing a required entry point");
+    g_nccl.lib = lib;
+    g_nccl_destroy = g_nccl.CommDestroy;
+    return SPHSM_OK;
+}
+#define NC(call)                                                                                        \
+    do {                                                                                                \
+        int r_ = (call);                                                                                \
+        if (r_ != 0) {                                                                                  \
+            std::string m_ = std::string(#call) + " failed: " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+            if (h) h->err = m_; else g_create_error = m_;                                               \
+            return SPHSM_ERR_COMM;                                                                      \
+        }                                                                                               \
+    } while (0)
+
+static int comm_alloc(sphsm_handle *h) {
+    if (h->msg_send[0]) return SPHSM_OK;
+    const int cap = h->send_cap;  // fixed at create (array room was allocated for it)
+    for (int k = 0; k < 2; k++) {
+        CU(cudaMalloc(&h->msg_send[k], msg_bytes(cap)));
+        CU(cudaMalloc(&h->msg_recv[k], msg_bytes(cap)));
+        CU(cudaMemset(h->msg_send[k], 0, 16));
+        CU(cudaMemset(h->msg_recv[k], 0, 16));
+    }
+    CU(cudaMalloc(&h->d_err, 4 * sizeof(int)));
+    CU(cudaMemset(h->d_err, 0, 4 * sizeof(int)));
+    CU(cudaMalloc(&h->d_meta, 8 * sizeof(int)));
+    CU(cudaMallocHost(&h->h_meta, 8 * sizeof(int)));
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_comm_unique_id(void *id128) {
+    sphsm_handle *h = nullptr;
+    if (!id128) return SPHSM_ERR_INVALID;
+    int rc = load_nccl(nullptr);
+    if (rc) return rc;
+    nccl_unique_id id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_comm_init(sphsm_handle *h, int nranks, int rank, const void *id128) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return SPHSM_ERR_INVALID;
+    if (h->prm.slab_axis < 0) return fail(h, SPHSM_ERR_INVALID, "create the handle with params.slab_axis = 0, 1 or 2 for multi-GPU");
+    if (h->prm.strict) return fail(h, SPHSM_ERR_INVALID, "strict mode is single-GPU only");
+    CU(cudaSetDevice(h->prm.device));
+    int rc = load_nccl(h);
+    if (rc) return rc;
+    nccl_unique_id id;
+    memcpy(&id, id128, sizeof id);
+    NC(g_nccl.CommInitRank(&h->nccl_comm, nranks, id, rank));
+    h->nccl_comm_red = h->nccl_comm;
+    // SPHSM_SPLIT_COMM=1: allreduce on a second communicator.  Off by default: measured at 8 GPUs / 8M it gained nothing (the
+    // allreduce queued behind exchange 1 still ends before the sort does) and the two NCCL kernels then share the SMs.
+    if (g_nccl.CommSplit && getenv("SPHSM_SPLIT_COMM")) NC(g_nccl.CommSplit(h->nccl_comm, 0, rank, &h->nccl_comm_red, nullptr));
+    h->comm_mode = 1; h->nranks = nranks; h->rank = rank;
+    return comm_alloc(h);
+}
+
+extern "C" int sphsm_comm_init_local(sphsm_handle **hs, int nranks) {
+    if (!hs || nranks < 1) return SPHSM_ERR_INVALID;
+    for (int r = 0; r < nranks; r++) {
+        sphsm_handle *h = hs[r];
+        if (!h) return SPHSM_ERR_INVALID;
+        if (h->prm.slab_axis < 0) return fail(h, SPHSM_ERR_INVALID, "create the handle with params.slab_axis = 0, 1 or 2 for multi-GPU");
+        if (h->prm.strict) return fail(h, SPHSM_ERR_INVALID, "strict mode is single-GPU only");
+        if (h->prm.device != hs[0]->prm.device || h->prm.capacity != hs[0]->prm.capacity)
+            return fail(h, SPHSM_ERR_INVALID, "a local group shares one device and one capacity");
+        CU(cudaSetDevice(h->prm.device));
+        h->comm_mode = 2; h->nranks = nranks; h->rank = r;
+        int rc = comm_alloc(h);
+        if (rc) return rc;
+    }
+    return SPHSM_OK;
+}
+
+// read the plane boundaries back (one 32-byte copy + stream sync) and set n / owned range from them
+static bool g_host_prof_early() { static const bool v = getenv("SPHSM_HOST_PROF") != nullptr; return v; }
+static double now_us_early() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+static int slab_meta_launch(sphsm_handle *h) {
+    const DevParams &d = h->dp;
+    LAUNCH(k_mg_meta, 1, 32, h->cell_start, d.num_cells, d.ga * d.gb, d.gcl, h->d_err, h->d_meta);
+    CU(cudaMemcpyAsync(h->h_meta, h->d_meta, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev_meta, h->stream));
+    return SPHSM_OK;
+}
+static int slab_meta_read(sphsm_handle *h) {
+    const double tw = g_host_prof_early() ? now_us_early() : 0.0;
+    CU(cudaEventSynchronize(h->ev_meta));  // (not the stream: work queued behind the read-back keeps running)
+    if (tw != 0.0) h->meta_wait_us += now_us_early() - tw;
+    const int *m = h->h_meta;
+    const char *what = m[5] ? "a particle crossed more than one cell plane in one step (or left the slab window)"
+                       : m[6] ? "halo message overflow: raise params.reserved[0] (halo capacity)" : nullptr;
+    const bool defer = h->comm_mode == 1 && h->nranks > 1 && h->slab_applied;  // inside an NCCL step: see local_error
+    if (what && !defer) return fail(h, SPHSM_ERR_COMM, what);
+    if (what && !h->local_error) {
+        h->local_error = 1;
+        h->local_error_msg = what;
+    }
+    if (defer && h->flag_pending) {
+        CU(cudaEventSynchronize(h->ev_flag));
+        h->flag_pending = false;
+        if (*h->h_flag != 0.0) h->peer_error = true;
+    }
+    h->n = m[0];
+    h->dp.n = m[0];
+    h->dp.own_begin = m[1];
+    h->b2 = m[2];
+    h->b3 = m[3];
+    h->dp.own_end = m[4];
+    return SPHSM_OK;
+}
+static int slab_meta(sphsm_handle *h) {
+    int rc = slab_meta_launch(h);
+    return rc ? rc : slab_meta_read(h);
+}
+
+extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
+    if (!h) return SPHSM_ERR_INVALID;
+    if (!h->comm_mode) return fail(h, SPHSM_ERR_COMM, "sphsm_comm_init first");
+    if (cell_lo < 0 || cell_hi > h->dp.gc || cell_hi - cell_lo < 1) return fail(h, SPHSM_ERR_INVALID, "slab must hold at least one cell plane of the grid");
+    CU(cudaSetDevice(h->prm.device));
+    DevParams &d = h->dp;
+    if (!d.slab_on) h->n_global = h->n;
+    d.slab_lo = cell_lo; d.slab_hi = cell_hi;
+    d.c_off = cell_lo - 1; d.gcl = cell_hi - cell_lo + 2;
+    d.num_cells = d.ga * d.gb * d.gcl;
+    d.slab_on = 1;
+    int rc;
+    if ((rc = setup_grid_buffers(h)) != 0) return rc;
+    // keep only the owned planes: dead entries sort into the limbo bucket and fall off the end
+    if (h->n > 0) {
+        d.own_begin = 0; d.own_end = h->n;
+        LAUNCH(k_mg_filter, cdiv(h->n, 256), 256, h->dp, h->cur);
+        h->inter_live = true;
+        if ((rc = build_grid(h, nullptr)) != 0) return rc;
+        if ((rc = slab_meta(h)) != 0) return rc;
+    }
+    h->grid_valid = false;
+    h->slab_applied = true;
+    h->local_error = 0; h->peer_error = false; h->failed = false; h->flag_pending = false;
+    if (h->d_err) CU(cudaMemsetAsync(h->d_err, 0, 4 * sizeof(int), h->stream));
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_comm_info(sphsm_handle *h, int out[8]) {
+    if (!h || !out) return SPHSM_ERR_INVALID;
+    out[0] = h->comm_mode; out[1] = h->nranks; out[2] = h->rank; out[3] = h->n;
+    out[4] = h->dp.own_begin; out[5] = h->dp.own_end; out[6] = h->send_cap; out[7] = h->dp.slab_on;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int cap, int *count) {
+    if (!h || !ids || !xyz || !count || cap < 0) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    const int first = h->dp.own_begin, nown = h->dp.own_end - h->dp.own_begin;
+    *count = nown;
+    if (nown > cap) return fail(h, SPHSM_ERR_CAPACITY, "output arrays smaller than the number of owned particles");
+    if (nown == 0) return SPHSM_OK;
+    int rc;
+    if ((rc = ensure_tmp(h, (size_t)nown * 3)) != 0 || (rc = ensure_itmp(h, (size_t)nown)) != 0) return rc;
+    LAUNCH(k_mg_owned_out, cdiv(nown, 256), 256, first, nown, h->cur, h->d_itmp, h->d_tmp);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ids, h->d_itmp, (size_t)nown * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(xyz, h->d_tmp, (size_t)nown * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SPHSM_OK;
+}
+
+// ---- collectives: NCCL (one process per GPU) --------------------------------------------------------------------
+static int comm_allreduce(sphsm_handle *h, int count) {
+    if (h->comm_mode != 1 || h->nranks == 1) return SPHSM_OK;  // single GPU; the local group sums between phases
+    NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm_red, h->launch_stream));
+    return SPHSM_OK;
+}
+static int nccl_exchange1(sphsm_handle *h) {
+    const size_t bytes = msg_bytes(h->send_cap);
+    NC(g_nccl.GroupStart());
+    if (h->rank > 0) {
+        NC(g_nccl.Send(h->msg_send[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->msg_recv[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
+    }
+    if (h->rank < h->nranks - 1) {
+        NC(g_nccl.Send(h->msg_send[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(h->msg_recv[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    return SPHSM_OK;
+}
+// boundary planes' pass-A results: V = (inter_vel, m/dens) and S = (pres, Vm), contiguous slot ranges on both sides
+static int nccl_exchange2(sphsm_handle *h, cudaStream_t st) {
+    const int ob = h->dp.own_begin, oe = h->dp.own_end, n = h->n;
+    NC(g_nccl.GroupStart());
+    if (h->rank > 0) {
+        NC(g_nccl.Send(h->cur.V + ob, (size_t)(h->b2 - ob) * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->cur.S + ob, (size_t)(h->b2 - ob) * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.V, (size_t)ob * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.S, (size_t)ob * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+    }
+    if (h->rank < h->nranks - 1) {
+        NC(g_nccl.Send(h->cur.V + h->b3, (size_t)(oe - h->b3) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->cur.S + h->b3, (size_t)(oe - h->b3) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.V + oe, (size_t)(n - oe) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->cur.S + oe, (size_t)(n - oe) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+    }
+    NC(g_nccl.GroupEnd());
+    const int halo = ob + (n - oe);  // VN (the dense copy of V.w) of the halo slots is rebuilt locally
+    if (halo > 0) {
+        cudaStream_t keep = h->launch_stream;
+        h->launch_stream = st;
+        int rc = [&]() -> int { LAUNCH(k_mg_halo_vn, cdiv(halo, 256), 256, ob, oe, n - oe, h->cur.V, h->cur.VN); return SPHSM_OK; }();
+        h->launch_stream = keep;
+        if (rc) return rc;
+    }
+    return SPHSM_OK;
+}
+
+// ---- the slab step as phases; every phase ends in the collective named by *coll ----------------------------------------
+enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE, COLL_ALLREDUCE_MOMENTS };
+static const int MG_PHASES = 6;
+
+static int mg_forked_allreduce(sphsm_handle *h);
+static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
+    const bool diag = h->prm.diagnostics != 0;
+    const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
+    int rc;
+    *coll = COLL_NONE; *count = 0;
+    switch (phase) {
+        case 0: {  // classify + pack
+            if (h->profiling) h->gt = new GroupTimer(h);
+            h->mom_begin = h->dp.own_begin;
+            h->mom_end = h->dp.own_end;
+            h->moments_forked = false;
+            if (h->comm_mode == 1 && !h->rest_dirty && !h->profiling) {
+                // the moment sums, their allreduce and the solve only need last step's owned slots: they run on the side
+                // stream beside the exchange, the hash and the sort, and rejoin before the gather applies the transform
+                CU(cudaEventRecord(h->ev_fork, h->stream));
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+                h->launch_stream = h->side_stream;
+                // (NCCL runs one communicator's operations in issue order whatever their streams: the allreduce is issued
+                // after exchange 1, in mg_forked_allreduce, so that the exchange does not queue behind the sums)
+                rc = moments_part(h);
+                h->launch_stream = h->stream;
+                if (rc) return rc;
+                h->moments_forked = true;
+                h->allreduce_pending = true;
+                if (h->nccl_comm_red != h->nccl_comm) {  // own communicator: nothing to queue behind
+                    if ((rc = mg_forked_allreduce(h)) != 0) return rc;
+                    h->allreduce_pending = false;
+                }
+            }
+            CU(cudaMemsetAsync(h->msg_send[0], 0, 16, h->stream));
+            CU(cudaMemsetAsync(h->msg_send[1], 0, 16, h->stream));
+            if (h->n > 0)
+                LAUNCH(k_mg_classify, cdiv(h->n, 256), 256, h->dp, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_send[0], h->send_cap),
+                       msg_view(h->msg_send[1], h->send_cap), h->send_cap, h->d_err);
+            if (h->gt) h->gt->end_group(KG_OTHER);
+            *coll = COLL_EXCH1;
+            return SPHSM_OK;
+        }
+        case 1: {  // unpack arrivals, hash + sort everything, cell table, plane boundaries
+            const int n0 = h->n, cap = h->send_cap;
+            if (n0 + 2 * cap > h->alloc_n) return fail(h, SPHSM_ERR_CAPACITY, "capacity too small for the halo arrivals");
+            LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, n0, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_recv[0], cap),
+                   msg_view(h->msg_recv[1], cap), cap);
+            h->n = n0 + 2 * cap;
+            h->dp.n = h->n;
+            h->mom_n = h->n;
+            if (h->gt) h->gt->end_group(KG_OTHER);
+            if ((rc = grid_sort(h, h->gt)) != 0) return rc;
+            if (!h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
+            h->reordered = false;
+            if (h->moments_forked && h->bounds_ready) {
+                // the gather needs the live count only as a bound: it is queued behind the read-back with the count taken
+                // from device memory, so the GPU is busy while the host waits for the plane boundaries
+                if ((rc = slab_meta_launch(h)) != 0) return rc;
+                CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+                h->moments_forked = false;
+                if ((rc = grid_finish(h, h->gt, diag ? 2 : 1, true, h->d_meta)) != 0) return rc;
+                h->reordered = true;
+                if ((rc = slab_meta_read(h)) != 0) return rc;
+            } else if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
+            if (!h->bounds_ready && !h->prm.reserved[1] && h->n > 0) {  // (the counting sort leaves every cell in canonical order)
+                // canonical in-cell order (ascending original id) where two ranks must agree slot by slot: the halo
+                // plane and the owned plane on either side of each face (arrivals were appended in atomic order)
+                const int src = h->sorted_buf, ob = h->dp.own_begin, oe = h->dp.own_end;
+                const bool one = h->b3 <= h->b2;  // slab of one or two planes: the ranges meet
+                const int r0 = 0, c0 = one ? h->n : (has_left ? h->b2 : 0);
+                const int r1 = h->b3, c1 = one ? 0 : (has_right ? h->n - h->b3 : 0);
+                (void)ob; (void)oe;
+                if (c0 > 0) LAUNCH(k_cell_order_fix, cdiv(c0, 128), 128, h->keys[src], h->vals[src], h->cur.ID, h->n, (uint32_t)h->dp.num_cells, r0, c0);
+                if (c1 > 0) LAUNCH(k_cell_order_fix, cdiv(c1, 128), 128, h->keys[src], h->vals[src], h->cur.ID, h->n, (uint32_t)h->dp.num_cells, r1, c1);
+            }
+            if (h->gt) h->gt->end_group(KG_GRID);
+            if (h->rest_dirty) {
+                if ((rc = rest_part1(h)) != 0) return rc;
+                *coll = COLL_ALLREDUCE; *count = 5;
+            }
+            return SPHSM_OK;
+        }
+        case 2:
+            if (h->rest_dirty) {
+                if ((rc = rest_part2(h)) != 0) return rc;
+                *coll = COLL_ALLREDUCE; *count = 90;
+            }
+            return SPHSM_OK;
+        case 3:
+            if (h->moments_forked || h->reordered) return SPHSM_OK;
+            if (h->rest_dirty && (rc = rest_part3(h)) != 0) return rc;
+            if ((rc = moments_part(h)) != 0) return rc;
+            *coll = COLL_ALLREDUCE_MOMENTS; *count = h->dp.quadratic ? 33 : 15;
+            return SPHSM_OK;
+        case 4: {  // solve, gather + stage 2, pass A
+            if (memcmp(&h->dp, &h->dp_uploaded, sizeof(DevParams)) != 0) {
+                h->dp_uploaded = h->dp;
+                CU(cudaMemcpyAsync(h->d_dp, &h->dp_uploaded, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
+            }
+            if (h->reordered) {
+            } else if (h->moments_forked) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+            else LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
+            h->moments_forked = false;
+            h->mom_n = 0;
+            if (h->gt) h->gt->end_group(KG_MOMENTS);
+            if (h->n > 0 && !h->reordered && (rc = grid_finish(h, h->gt, diag ? 2 : 1, true)) != 0) return rc;
+            const int ob = h->dp.own_begin, oe = h->dp.own_end;
+            // NCCL mode with at least three owned planes: pass A on the two boundary planes first, their V / S records travel
+            // on the side stream while the interior planes are computed here (and pass B's interior after them)
+            h->split = h->comm_mode == 1 && h->nranks > 1 && !h->profiling && h->b2 < h->b3 && g_pass_gen >= 4;
+            if (h->split) {
+                // side stream (high priority): pass A on the two boundary planes -> exchange 2 -> pass B on them;
+                // main stream: pass A, then pass B on the interior planes.  Cross dependencies: pass B's interior reads the
+                // boundary planes' pass-A records (ev_bnd), pass B's boundary reads the interior's (ev_int).
+                CU(cudaEventRecord(h->ev_fork, h->stream));
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+                h->launch_stream = h->side_stream;
+                rc = launch_pass_a(h, ob, oe, h->b2, h->b3);
+                h->launch_stream = h->stream;
+                if (rc) return rc;
+                CU(cudaEventRecord(h->ev_bnd, h->side_stream));
+                if ((rc = launch_pass_a(h, h->b2, h->b3)) != 0) return rc;  // (queued before the NCCL calls: they take host time)
+                CU(cudaEventRecord(h->ev_int, h->stream));
+                CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
+                if ((rc = launch_pass_b(h, h->b2, h->b3, diag)) != 0) return rc;
+                if (g_host_prof_early() && h->pev[4]) CU(cudaEventRecord(h->pev[4], h->side_stream));
+                rc = nccl_exchange2(h, h->side_stream);
+                if (g_host_prof_early() && h->pev[5]) CU(cudaEventRecord(h->pev[5], h->side_stream));
+                return rc;
+            }
+            if ((rc = launch_pass_a(h, ob, oe)) != 0) return rc;
+            if (h->gt) h->gt->end_group(KG_PASS_A);
+            *coll = COLL_EXCH2;
+            return SPHSM_OK;
+        }
+        case 5: {  // pass B on the owned slots
+            if (h->gt) h->gt->end_group(KG_OTHER);  // exchange 2
+            const int ob = h->dp.own_begin, oe = h->dp.own_end;
+            if (h->split) {  // interior planes need no halo record; the boundary planes wait for exchange 2 (stream order)
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_int, 0));  // (pass B's interior was queued in phase 4)
+                h->launch_stream = h->side_stream;
+                rc = launch_pass_b(h, ob, oe, diag, h->b2, h->b3);
+                h->launch_stream = h->stream;
+                if (rc) return rc;
+                CU(cudaEventRecord(h->ev_join, h->side_stream));
+                CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+            } else if ((rc = launch_pass_b(h, ob, oe, diag)) != 0) return rc;
+            std::swap(h->cur.P, h->alt.P);
+            if (h->gt) {
+                h->gt->end_group(KG_PASS_B);
+                h->gt->finish();
+                delete h->gt;
+                h->gt = nullptr;
+            }
+            CU(cudaGetLastError());
+            h->grid_valid = false;
+            h->inter_live = false;
+            h->total_steps++;
+            *coll = COLL_DONE;
+            return SPHSM_OK;
+        }
+    }
+    return fail(h, SPHSM_ERR_INVALID, "bad phase");
+}
+
+static int mg_check(sphsm_handle *h) {
+    if (!h->slab_applied) return fail(h, SPHSM_ERR_COMM, "sphsm_comm_set_slab must be applied after the particle set is uploaded");
+    if (h->stage_timing) return fail(h, SPHSM_ERR_INVALID, "stage timing is single-GPU only");
+    return SPHSM_OK;
+}
+
+// second half of the forked moment chain: allreduce + solve on the side stream, then the join event
+static int mg_forked_allreduce(sphsm_handle *h) {
+    h->launch_stream = h->side_stream;
+    int rc = moment_allreduce(h);
+    if (!rc) rc = [&]() -> int { LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm); return SPHSM_OK; }();
+    h->launch_stream = h->stream;
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev_join, h->side_stream));
+    return SPHSM_OK;
+}
+
+// SPHSM_HOST_PROF=1: host-side time of the slab step per phase (kernel launches / NCCL calls / the read-back wait), printed
+// by rank 0 every 64 steps — tells a launch-bound step from a device-bound one
+static const bool g_host_prof = getenv("SPHSM_HOST_PROF") != nullptr;
+static double now_us() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+static int mg_step_nccl(sphsm_handle *h) {
+    int rc, coll, count;
+    if ((rc = mg_check(h)) != 0) return rc;
+    static double acc[MG_PHASES + 1][2];
+    static int steps_seen = 0;
+    for (int ph = 0; ph < MG_PHASES; ph++) {
+        const double t0 = g_host_prof ? now_us() : 0.0;
+        if ((rc = mg_phase(h, ph, &coll, &count)) != 0) return rc;
+        const double t1 = g_host_prof ? now_us() : 0.0;
+        if (coll == COLL_EXCH1) {
+            if (g_host_prof) {
+                for (int k = 0; k < 8; k++)
+                    if (!h->pev[k]) CU(cudaEventCreate(&h->pev[k]));
+                CU(cudaEventRecord(h->pev[0], h->stream));
+            }
+            rc = nccl_exchange1(h);
+            if (g_host_prof) CU(cudaEventRecord(h->pev[1], h->stream));
+            if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[2], h->side_stream));
+            if (!rc && h->moments_forked && h->allreduce_pending) rc = mg_forked_allreduce(h);
+            h->allreduce_pending = false;
+            if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[3], h->side_stream));
+        }
+        else if (coll == COLL_ALLREDUCE) rc = comm_allreduce(h, count);
+        else if (coll == COLL_ALLREDUCE_MOMENTS) rc = moment_allreduce(h);
+        else if (coll == COLL_EXCH2) rc = nccl_exchange2(h, h->stream);
+        if (rc) return rc;
+        if (g_host_prof) {
+            acc[ph][0] += t1 - t0;
+            acc[ph][1] += now_us() - t1;
+        }
+    }
+    if (h->peer_error) {  // some rank (maybe this one) failed in the previous step: every rank stops here
+        h->failed = true;
+        return fail(h, SPHSM_ERR_COMM, h->local_error ? h->local_error_msg.c_str()
+                                                      : "another rank of the slab group reported a step error (its sphsm_last_error has the cause)");
+    }
+    if (g_host_prof && h->pev[5] && h->split) {  // device-side durations of the three collectives (this serialises the steps)
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaStreamSynchronize(h->side_stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->pev[0], h->pev[1]) == cudaSuccess) h->pacc[0] += ms * 1e3;
+        if (cudaEventElapsedTime(&ms, h->pev[2], h->pev[3]) == cudaSuccess) h->pacc[1] += ms * 1e3;
+        if (cudaEventElapsedTime(&ms, h->pev[4], h->pev[5]) == cudaSuccess) h->pacc[2] += ms * 1e3;
+        if (cudaEventElapsedTime(&ms, h->pev[0], h->pev[5]) == cudaSuccess) h->pacc[3] += ms * 1e3;
+        cudaGetLastError();
+    }
+    if (g_host_prof && ++steps_seen % 64 == 0) {
+        fprintf(stderr, "[sphsm dev prof rank %d, cumulative us over %d steps] exch1 %.0f allreduce+solve %.0f exch2+vn %.0f exch1-start..exch2-end %.0f\n",
+                h->rank, steps_seen, h->pacc[0], h->pacc[1], h->pacc[2], h->pacc[3]);
+    }
+    if (g_host_prof && steps_seen % 64 == 0 && h->rank == 0) {
+        fprintf(stderr, "[sphsm host prof, us/step over %d steps] ", steps_seen);
+        double tot = 0;
+        for (int ph = 0; ph < MG_PHASES; ph++) {
+            fprintf(stderr, "ph%d %.1f+%.1f  ", ph, acc[ph][0] / steps_seen, acc[ph][1] / steps_seen);
+            tot += acc[ph][0] + acc[ph][1];
+        }
+        fprintf(stderr, "total %.1f (read-back wait %.1f)\n", tot / steps_seen, h->meta_wait_us / steps_seen);
+    }
+    return SPHSM_OK;
+}
+
+// virtual ranks: the same phases in lockstep over handles that share one device; collectives are device copies
+extern "C" int sphsm_step_group(sphsm_handle **hs, int nranks, int nsteps) {
+    if (!hs || nranks < 1 || nsteps < 0) return SPHSM_ERR_INVALID;
+    for (int r = 0; r < nranks; r++) {
+        sphsm_handle *h = hs[r];
+        if (!h || h->comm_mode != 2 || h->nranks != nranks || h->rank != r) return fail(h, SPHSM_ERR_COMM, "not the local group made by sphsm_comm_init_local");
+        int rc = mg_check(h);
+        if (rc) return rc;
+    }
+    sphsm_handle *h = hs[0];
+    CU(cudaSetDevice(h->prm.device));
+    std::vector<int> coll(nranks), count(nranks);
+    std::vector<double> sum(128), part(128);
+    for (int s = 0; s < nsteps; s++) {
+        for (int ph = 0; ph < MG_PHASES; ph++) {
+            for (int r = 0; r < nranks; r++) {
+                int rc = mg_phase(hs[r], ph, &coll[r], &count[r]);
+                if (rc) return rc;
+                if (coll[r] != coll[0] || count[r] != count[0]) return fail(hs[r], SPHSM_ERR_COMM, "ranks disagree on the phase program");
+            }
+            for (int r = 0; r < nranks; r++) CU(cudaStreamSynchronize(hs[r]->stream));
+            if (coll[0] == COLL_EXCH1) {
+                const size_t bytes = msg_bytes(h->send_cap);
+                for (int r = 0; r < nranks; r++) {
+                    if (r > 0) CU(cudaMemcpy(hs[r]->msg_recv[0], hs[r - 1]->msg_send[1], bytes, cudaMemcpyDeviceToDevice));
+                    if (r < nranks - 1) CU(cudaMemcpy(hs[r]->msg_recv[1], hs[r + 1]->msg_send[0], bytes, cudaMemcpyDeviceToDevice));
+                }
+            } else if (coll[0] == COLL_ALLREDUCE || coll[0] == COLL_ALLREDUCE_MOMENTS) {
+                const int c = count[0];
+                std::fill(sum.begin(), sum.end(), 0.0);
+                for (int r = 0; r < nranks; r++) {
+                    CU(cudaMemcpy(part.data(), hs[r]->totals, c * sizeof(double), cudaMemcpyDeviceToHost));
+                    for (int k = 0; k < c; k++) sum[k] += part[k];
+                }
+                for (int r = 0; r < nranks; r++) CU(cudaMemcpy(hs[r]->totals, sum.data(), c * sizeof(double), cudaMemcpyHostToDevice));
+            } else if (coll[0] == COLL_EXCH2) {
+                for (int r = 0; r + 1 < nranks; r++) {  // face between rank r (left) and rank r + 1 (right)
+                    sphsm_handle *a = hs[r], *b = hs[r + 1];
+                    const int na = a->dp.own_end - a->b3, nb_halo = b->dp.own_begin;       // a's last owned plane -> b's left halo
+                    const int nb = b->b2 - b->dp.own_begin, na_halo = a->n - a->dp.own_end;  // b's first owned plane -> a's right halo
+                    if (na != nb_halo || nb != na_halo) return fail(a, SPHSM_ERR_COMM, "boundary plane populations differ across a slab face");
+                    CU(cudaMemcpy(b->cur.V, a->cur.V + a->b3, (size_t)na * sizeof(float4), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(b->cur.S, a->cur.S + a->b3, (size_t)na * sizeof(float2), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(b->cur.VN, a->cur.VN + a->b3, (size_t)na * sizeof(float), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(a->cur.V + a->dp.own_end, b->cur.V + b->dp.own_begin, (size_t)nb * sizeof(float4), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(a->cur.S + a->dp.own_end, b->cur.S + b->dp.own_begin, (size_t)nb * sizeof(float2), cudaMemcpyDeviceToDevice));
+                    CU(cudaMemcpy(a->cur.VN + a->dp.own_end, b->cur.VN + b->dp.own_begin, (size_t)nb * sizeof(float), cudaMemcpyDeviceToDevice));
+                }
+            }
+        }
+    }
+    return SPHSM_OK;
+}

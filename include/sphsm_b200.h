@@ -224,6 +224,14 @@ int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int cap, int *co
 int sphsm_comm_init_local(sphsm_handle **handles, int nranks);
 int sphsm_step_group(sphsm_handle **handles, int nranks, int nsteps);
 
+/* Process-wide kernel-path switches for tests and tuning (no reference counterpart): "pass" = 6 (block-staged neighbour
+ * passes, the default) | 4 (the gathered passes they are bit-identical to); "stage6" = 1 | 0 (0: every block of the
+ * generation-6 kernels takes its in-kernel gathered path); "t6" = 128 | 64 targets per block; "b_step6" = 2 | 4 candidates
+ * per iteration of the force pass; "warp_path" = 1 | 0 (0: small dense sets take the thread-per-particle kernels too).  The
+ * same switches are read once from $SPHSM_PASS, $SPHSM_STAGE6, $SPHSM_T6, $SPHSM_B_STEP6, $SPHSM_WARP_PATH.  "pass", "stage6",
+ * "t6" and "b_step6" change no result bit; "warp_path" changes the order of the floating-point sums. */
+int sphsm_tune(const char *name, int value);
+
 const char *sphsm_last_error(sphsm_handle *h);
 
 #ifdef __cplusplus

@@ -81,6 +81,7 @@ SYMBOLS = {
     "sphsm_download_owned": (C.c_int, [_H, _IP, _FP, C.c_int, _IP]),
     "sphsm_comm_init_local": (C.c_int, [C.POINTER(_H), C.c_int]),
     "sphsm_step_group": (C.c_int, [C.POINTER(_H), C.c_int, C.c_int]),
+    "sphsm_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "sphsm_last_error": (C.c_char_p, [_H]),
 }
 

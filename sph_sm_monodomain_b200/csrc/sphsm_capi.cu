@@ -18,11 +18,9 @@
 
 #include "sphsm_comm.cuh"
 #include "sphsm_pass.cuh"
-#include "sphsm_pass2.cuh"
-#include "sphsm_pass3.cuh"
 #include "sphsm_pass4.cuh"
 #include "sphsm_pass4w.cuh"
-#include "sphsm_pass5.cuh"
+#include "sphsm_pass6.cuh"
 #include "sphsm_sm.cuh"
 #include "sphsm_sort.cuh"
 #include "sphsm_types.cuh"
@@ -47,7 +45,7 @@ static const char *kGroupNames[SPHSM_NUM_KERNEL_GROUPS] = {"hash", "radix_sort",
 struct sphsm_handle {
     sphsm_params prm;
     DevParams dp;
-    DevParams *d_dp = nullptr;  // global-memory copy of dp for the fast passes (sphsm_pass2.cuh)
+    DevParams *d_dp = nullptr;  // global-memory copy of dp for the fast passes (loop invariants pinned in registers, sphsm_pass4.cuh)
     DevParams dp_uploaded{};
     int n = 0;
     cudaStream_t stream = nullptr;
@@ -71,6 +69,8 @@ struct sphsm_handle {
     bool split = false;                    // slab step: exchange 2 in flight on the side stream beside the interior planes
     Arrays cur{}, alt{};
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
+    uint32_t *skeys = nullptr;       // counting sort: the cell key of every slot, in slot order (k_cell_scatter)
+    uint32_t *key_sorted = nullptr;  // what the neighbour passes read: skeys, or the radix sort's sorted key buffer
     uint32_t *ghist = nullptr, *tile_state = nullptr, *tile_counter = nullptr;
     int sorted_buf = 0;  // which keys[] / vals[] hold the sorted result
     uint32_t *cell_count = nullptr, *tile_sums = nullptr;  // counting sort: per-cell counts (kept zero between steps), scan scratch
@@ -146,10 +146,27 @@ struct sphsm_handle {
 
 // SPHSM_SYNC_DEBUG=1 in the environment synchronises after every launch and names the kernel that faulted
 static const bool g_sync_debug = getenv("SPHSM_SYNC_DEBUG") != nullptr;
-// SPHSM_PASS selects the generation of the fast-path neighbour passes: 4 = sphsm_pass4.cuh (production), 2 = sphsm_pass2.cuh
-// (its predecessor), 3 = the experimental warp-staged passes (sphsm_pass3.cuh; correct, but measured 2x slower at 8M:
-// profiles/r01_v5_staged_*.json)
-static const int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 4;
+// SPHSM_PASS selects the fast-path neighbour passes: 6 = sphsm_pass6.cuh (production: block-staged stencil spans), 4 = the gathered
+// thread-per-particle passes of sphsm_pass4.cuh (the bit-identical reference the staged passes are tested against).
+// SPHSM_STAGE6=0 makes every block of the generation-6 kernels take their in-kernel gathered path; SPHSM_T6 = 64 | 128 targets per
+// block; SPHSM_B_STEP6 = 2 | 4 candidates per iteration of pass B's phase 1.
+// The same four switches can be changed at run time with sphsm_tune("pass" | "stage6" | "t6" | "b_step6", value) (tests).
+static int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 6;
+static int g_stage6 = getenv("SPHSM_STAGE6") ? atoi(getenv("SPHSM_STAGE6")) : 1;
+static int g_t6 = getenv("SPHSM_T6") ? atoi(getenv("SPHSM_T6")) : 128;
+static int g_b_step6 = getenv("SPHSM_B_STEP6") ? atoi(getenv("SPHSM_B_STEP6")) : 2;
+static int g_warp_path = getenv("SPHSM_WARP_PATH") ? atoi(getenv("SPHSM_WARP_PATH")) : 1;  // 0: small dense sets take the thread-per-particle kernels too
+extern "C" int sphsm_tune(const char *name, int value) {
+    if (!name) return SPHSM_ERR_INVALID;
+    const std::string n(name);
+    if (n == "pass" && (value == 4 || value == 6)) g_pass_gen = value;
+    else if (n == "stage6" && (value == 0 || value == 1)) g_stage6 = value;
+    else if (n == "t6" && (value == 64 || value == 128)) g_t6 = value;
+    else if (n == "b_step6" && (value == 2 || value == 4)) g_b_step6 = value;
+    else if (n == "warp_path" && (value == 0 || value == 1)) g_warp_path = value;
+    else return SPHSM_ERR_INVALID;
+    return SPHSM_OK;
+}
 #define LAUNCH(kern, grid, block, ...)                                                                  \
     do {                                                                                                \
         if (!h->dry_run) kern<<<(grid), (block), 0, h->launch_stream>>>(__VA_ARGS__);                   \
@@ -380,6 +397,7 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
         CU(cudaMalloc(&h->keys[k], (size_t)cap * sizeof(uint32_t)));
         CU(cudaMalloc(&h->vals[k], (size_t)cap * sizeof(uint32_t)));
     }
+    CU(cudaMalloc(&h->skeys, ((size_t)cap + 8) * sizeof(uint32_t)));
     h->max_tiles = cdiv(cap, SORT_TILE);
     CU(cudaMalloc(&h->ghist, MAX_SORT_PASSES * RADIX * sizeof(uint32_t)));
     CU(cudaMalloc(&h->tile_state, (size_t)MAX_SORT_PASSES * h->max_tiles * RADIX * sizeof(uint32_t)));
@@ -412,6 +430,7 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     free_arrays(h->cur, true);
     free_arrays(h->alt, false);
     for (int k = 0; k < 2; k++) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
+    cudaFree(h->skeys);
     cudaFree(h->cell_count); cudaFree(h->tile_sums); cudaFree(h->big_cells); cudaFree(h->big_count);
     cudaFree(h->ghist); cudaFree(h->tile_state); cudaFree(h->tile_counter); cudaFree(h->cell_start); cudaFree(h->slot_of);
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);

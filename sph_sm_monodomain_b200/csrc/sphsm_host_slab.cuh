@@ -373,7 +373,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             const int ob = h->dp.own_begin, oe = h->dp.own_end;
             // NCCL mode with at least three owned planes: pass A on the two boundary planes first, their V / S records travel
             // on the side stream while the interior planes are computed here (and pass B's interior after them)
-            h->split = h->comm_mode == 1 && h->nranks > 1 && !h->profiling && h->b2 < h->b3 && g_pass_gen >= 4;
+            h->split = h->comm_mode == 1 && h->nranks > 1 && !h->profiling && h->b2 < h->b3;
             if (h->split) {
                 // side stream (high priority): pass A on the two boundary planes -> exchange 2 -> pass B on them;
                 // main stream: pass A, then pass B on the interior planes.  Cross dependencies: pass B's interior reads the

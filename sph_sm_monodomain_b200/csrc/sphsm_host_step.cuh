@@ -63,7 +63,8 @@ static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt) {
     LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
     LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles, h->big_count);
     LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start);
-    LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0]);
+    LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0], h->skeys);
+    h->key_sorted = h->skeys;
     LAUNCH(k_cell_sort_ids, cdiv(h->dp.num_cells, 256), 256, h->cell_start, h->vals[0], h->cur.ID, h->dp.num_cells, h->big_cells, h->big_count);
     LAUNCH(k_cell_sort_big, 64, 256, h->cell_start, h->vals[0], h->vals[1], h->cur.ID, h->big_cells, h->big_count);
     h->sorted_buf = 0;
@@ -93,6 +94,7 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
         src ^= 1;
     }
     h->sorted_buf = src;
+    h->key_sorted = h->keys[src];
     // in-cell order = ascending original index: the reference's bucket order (strict mode), and the canonical order that
     // makes both sides of a slab face hold the shared plane identically (slab mode; reserved[1] forces it on one GPU)
     // (the slab step orders only the planes on either side of its faces, once the plane boundaries are known)
@@ -291,24 +293,60 @@ static int run_stage(sphsm_handle *h, int stage) {
 // condition: at least 3 particles per occupied cell, estimated on the host from the positions as they were handed in
 // (note_host_positions; the reference's sets have 4.9-5.1, lattices of spacing 0.9 h have 1.4).
 static bool warp_path(const sphsm_handle *h) {
-    static const bool off = getenv("SPHSM_WARP_PATH") && atoi(getenv("SPHSM_WARP_PATH")) == 0;
-    if (off || g_pass_gen < 4) return false;
+    if (!g_warp_path) return false;
     static const int limit = getenv("SPHSM_WARP_PATH_MAX") ? atoi(getenv("SPHSM_WARP_PATH_MAX")) : WARP_PATH_MAX;
     const int n = h->dp.slab_on ? h->n_global : h->n;
     if (n > limit || h->host_cells.empty()) return false;
     return (double)n >= 3.0 * (double)h->host_cells.size();  // >= 3 particles per occupied cell: rows long enough for a warp
 }
 // slots [begin, end) minus the hole [hole_b, hole_e) (generation-4 kernels only)
+// blocks of a generation-6 launch: the two ranges on either side of the hole are cut into blocks separately (block_range6)
+static int grid6(int begin, int end, int hole_b, int hole_e, int T) {
+    if (hole_e > hole_b) return cdiv(hole_b - begin, T) + cdiv(end - hole_e, T);
+    return cdiv(end - begin, T);
+}
+template <class K>
+static int prepare6(sphsm_handle *h, K kern, unsigned bytes) {  // dynamic shared memory beyond 48 KB needs the opt-in; carve-out: all of it
+    static std::unordered_set<const void *> done;
+    if (done.count((const void *)kern)) return SPHSM_OK;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    done.insert((const void *)kern);
+    return SPHSM_OK;
+}
+#define LAUNCH6(kern, T, WITH4, grid, ...)                                                                              \
+    do {                                                                                                                \
+        const unsigned bytes_ = Lay6<T, WITH4>::BYTES;                                                                  \
+        int rc_ = prepare6(h, kern, bytes_);                                                                            \
+        if (rc_) return rc_;                                                                                            \
+        if (!h->dry_run) kern<<<(grid), (T), bytes_, h->launch_stream>>>(__VA_ARGS__);                                   \
+        h->launches++;                                                                                                  \
+        if (g_sync_debug) {                                                                                             \
+            cudaError_t e_ = cudaStreamSynchronize(h->launch_stream);                                                   \
+            if (e_ != cudaSuccess) {                                                                                    \
+                h->err = std::string("kernel ") + #kern + " failed: " + cudaGetErrorString(e_);                         \
+                fprintf(stderr, "[sphsm] %s\n", h->err.c_str());                                                        \
+                return SPHSM_ERR_CUDA;                                                                                  \
+            }                                                                                                           \
+        }                                                                                                               \
+    } while (0)
+
+// slots [begin, end) minus the hole [hole_b, hole_e)
 static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0) {
     const int count = end - begin - (hole_e - hole_b);
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
     if (warp_path(h)) LAUNCH(k_pass_a4w, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->cell_start, count);
-    else if (g_pass_gen == 5) LAUNCH(k_pass_a5, cdiv(cdiv(count, 2), PT5), PT5, d, h->d_dp, h->cur, h->cell_start, count);
     else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start);
-    else if (g_pass_gen == 2) LAUNCH(k_pass_a2, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
-    else LAUNCH(k_pass_a3, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->cell_start);
+    else if (g_t6 == 64) LAUNCH6(k_pass_a6<64>, 64, false, grid6(begin, end, hole_b, hole_e, 64), d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6);
+    else LAUNCH6(k_pass_a6<128>, 128, false, grid6(begin, end, hole_b, hole_e, 128), d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6);
+    return SPHSM_OK;
+}
+template <int T, int STEP>
+static int launch_pass_b6(sphsm_handle *h, const DevParams &d, int grid, bool diag, uint32_t *nk, uint32_t *nr, uint32_t *ncnt) {
+    if (diag) LAUNCH6((k_pass_b6<T, STEP, true>), T, true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, g_stage6);
+    else LAUNCH6((k_pass_b6<T, STEP, false>), T, true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, g_stage6);
     return SPHSM_OK;
 }
 static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hole_b = 0, int hole_e = 0, bool file_counts = false) {
@@ -320,15 +358,15 @@ static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hol
     if (warp_path(h)) {
         if (diag) LAUNCH(k_pass_b4w<true>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count);
         else LAUNCH(k_pass_b4w<false>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count);
-    } else if (g_pass_gen == 4 || g_pass_gen == 5) {
+    } else if (g_pass_gen == 4) {
         if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt);
         else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt);
-    } else if (g_pass_gen == 2) {
-        if (diag) LAUNCH(k_pass_b2<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b2<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
+    } else if (g_t6 == 64) {
+        const int grid = grid6(begin, end, hole_b, hole_e, 64);
+        return g_b_step6 == 4 ? launch_pass_b6<64, 4>(h, d, grid, diag, nk, nr, ncnt) : launch_pass_b6<64, 2>(h, d, grid, diag, nk, nr, ncnt);
     } else {
-        if (diag) LAUNCH(k_pass_b3<true>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
-        else LAUNCH(k_pass_b3<false>, cdiv(count, PT), PT, d, h->d_dp, h->cur, h->alt.P, h->cell_start);
+        const int grid = grid6(begin, end, hole_b, hole_e, 128);
+        return g_b_step6 == 4 ? launch_pass_b6<128, 4>(h, d, grid, diag, nk, nr, ncnt) : launch_pass_b6<128, 2>(h, d, grid, diag, nk, nr, ncnt);
     }
     return SPHSM_OK;
 }
@@ -381,7 +419,7 @@ static int fused_step(sphsm_handle *h) {
         gt.end_group(KG_PASS_A);
         // the counting sort of the NEXT step starts inside pass B: each thread files the key / rank / count of the position it
         // has just integrated (valid until anything else moves particles: drop_counts)
-        const bool file_counts = g_pass_gen >= 4 && h->comm_mode == 0 && use_counting_sort(h);
+        const bool file_counts = h->comm_mode == 0 && use_counting_sort(h);
         if ((rc = launch_pass_b(h, 0, n, diag, 0, 0, file_counts)) != 0) return rc;
         h->counts_ready = file_counts;
     }
@@ -434,9 +472,9 @@ static std::string step_signature(const sphsm_handle *h) {
     put(&h->dp, sizeof(DevParams));
     put(&h->prm, sizeof(sphsm_params));
     const void *ptrs[] = {h->cell_start, h->cell_count, h->tile_sums, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->big_cells, h->big_count,
-                          h->sm, h->partial, h->totals, h->d_dp, h->ghist, h->tile_state, h->tile_counter, h->scratch};
+                          h->sm, h->partial, h->totals, h->d_dp, h->ghist, h->tile_state, h->tile_counter, h->scratch, h->skeys};
     put(ptrs, sizeof(ptrs));
-    const int flags[] = {h->counts_ready, h->bounds_ready, h->sorted_buf, g_pass_gen, h->red_blocks, h->sort_passes, (int)h->grid_valid};
+    const int flags[] = {h->counts_ready, h->bounds_ready, h->sorted_buf, g_pass_gen, h->red_blocks, h->sort_passes, (int)h->grid_valid, (int)warp_path(h), g_stage6, g_t6, g_b_step6};
     put(flags, sizeof(flags));
     return sig;
 }

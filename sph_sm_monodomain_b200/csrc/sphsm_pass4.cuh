@@ -1,6 +1,6 @@
 // sphsm_pass4.cuh — the production (fast-path) neighbour passes, fourth generation.
 //
-// Same two-phase scheme as sphsm_pass2.cuh (phase 1 sweeps the stencil rows and lists the in-range candidates per lane
+// Two-phase scheme (phase 1 sweeps the stencil rows and lists the in-range candidates per lane
 // in shared memory, phase 2 does the heavy in-range terms with every lane busy), rebuilt around the instruction counts of
 // the r01_v6 ncu source pages (pass B: 2594 warp instructions per 32 particles, 59 % in the candidate-pair loop at 68
 // instructions per pair, 250 in the per-row window setup, 520 in prologue + epilogue):
@@ -16,10 +16,18 @@
 //     divisions (the voltage side keeps the reference's exact operations, see integrate_fast).
 // Neighbour-set membership stays bit-exact: r^2 without FMA against the same host-computed thresholds.
 #pragma once
-#include "sphsm_pass2.cuh"
+#include "sphsm_pass.cuh"
 #include "sphsm_types.cuh"
 
 namespace sphsm {
+
+constexpr int LIST_K = 16;  // in-range list entries per lane between drains
+
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ float sqrt_ftz(float x) {
     float y;
@@ -30,6 +38,17 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// a / b rounded to nearest, identical to __fdiv_rn.  A zero numerator sends the compiler's division sequence down its slow path
+// (FCHK flags it; ncu r01_v8: one CALL of ~50 instructions per warp in pass B for stim * dt / mass with stim == 0, the common
+// case), so that case is answered directly: +-0 / b = +-0 for b > 0.
+__device__ __forceinline__ float div_rn_z(float a, float b) { return (a == 0.0f && b > 0.0f) ? a : __fdiv_rn(a, b); }
+
+// the k-th target slot of a launch over [own_begin, own_end) minus the hole
+__device__ __forceinline__ int launch_slot(const DevParams &p, int k) {
+    int i = p.own_begin + k;
+    if (i >= p.hole_begin) i += p.hole_len;
+    return i;
 }
 
 // The in-range list lives at 32-bit shared-memory addresses held in a register (`lofs`, bytes): ptxas re-materialises the
@@ -114,6 +133,22 @@ __device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict
     drain(lofs);
 }
 
+// pass A's per-particle tail, shared by every fast-path kernel: the extra self term, pressure (cpp:483-503) and the records pass B
+// reads.  S = (pres, dens): pass B takes its own density from here, so VEL is neither read nor rewritten between the gather
+// and pass B's final store.
+__device__ __forceinline__ void pass_a_finish(const DevParams &p, const Arrays &a, int i, const float4 pi, const float4 ci, float dens, float pvx,
+                                              float pvy, float pvz) {
+    const float4 e4 = a.E[i];
+    dens = fmaf(pi.w, p.poly6_self, dens);                           // the extra self term, cpp:483 (Q1)
+    float pres = p.K * (dens - p.rho0) - e4.x * p.voltage_constant;  // cpp:486-491
+    if (e4.w > 0.0f) pres = fminf(fmaxf(pres, -p.max_pressure), p.max_pressure);
+    else pres = -0.0f;  // cpp:493-503 (Q2)
+    a.S[i] = make_float2(pres, dens);
+    const float vol = __fdiv_rn(pi.w, dens);  // np->mass / np->dens as pass B reads it, cpp:551
+    a.V[i] = make_float4(fmaf(pvx, p.mix, ci.x), fmaf(pvy, p.mix, ci.y), fmaf(pvz, p.mix, ci.z), vol);
+    a.VN[i] = vol;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
 __global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
@@ -183,16 +218,7 @@ __global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_consta
                 lo = lbase;
             });
     }
-    const float4 e4 = a.E[i];
-    dens = fmaf(pi.w, p.poly6_self, dens);                           // the extra self term, cpp:483 (Q1)
-    float pres = p.K * (dens - p.rho0) - e4.x * p.voltage_constant;  // cpp:486-491
-    if (e4.w > 0.0f) pres = fminf(fmaxf(pres, -p.max_pressure), p.max_pressure);
-    else pres = -0.0f;  // cpp:493-503 (Q2)
-    a.VEL[i].w = dens;
-    a.S[i] = make_float2(pres, e4.x);
-    const float vol = __fdiv_rn(pi.w, dens);  // np->mass / np->dens as pass B reads it, cpp:551
-    a.V[i] = make_float4(fmaf(pvx, p.mix, ci.x), fmaf(pvy, p.mix, ci.y), fmaf(pvz, p.mix, ci.z), vol);
-    a.VN[i] = vol;
+    pass_a_finish(p, a, i, pi, ci, dens, pvx, pvy, pvz);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -222,7 +248,7 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
         y = fmaf(vy, p.dt, y);
         z = fmaf(vz, p.dt, z);
     }
-    Vm = SPHSM_FAST_ODE ? fmaf(inter_vm, dtm, Vm) : Vm + (inter_vm * p.dt) / mass;  // cpp:612
+    Vm = SPHSM_FAST_ODE ? fmaf(inter_vm, dtm, Vm) : Vm + div_rn_z(inter_vm * p.dt, mass);  // cpp:612
     Vm = fminf(fmaxf(Vm, -p.max_voltage), p.max_voltage);
     // walls (cpp:620-646); the final bounds.clamp (m3Bounds.h:84-88) cannot move a position that passed them
     if (x < 0.0f) { vx *= p.wall_hit; x = 0.0f; }
@@ -236,20 +262,24 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
 // pass B's per-particle tail, shared by the thread-per-particle and the warp-per-particle kernels: acceleration, Inter_Vm
 // (cpp:568-571), Update_Properties (cpp:602-649), and — when cell_count is given — the next step's counting-sort input.
 // e4 = (Vm, Iion, w, stim) AFTER the ionic model; L = the SPH Laplacian sum of Vm.
+// dens = this particle's new density (S.y, written by pass A); the old velocity is not an input of the step's last stage
+// (cpp:605: vel = inter_vel + acc * dt / mass), so VEL is written here without having been read.
 template <bool DIAG>
 __device__ __forceinline__ void pass_b_finish(const DevParams &p, const Arrays &a, float4 *__restrict__ Pout, const int i, const float4 pi,
-                                              const float4 vi, float4 e4, float ax, float ay, float az, const float L, const float inv_mass,
-                                              uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count) {
-    float4 v4 = a.VEL[i];
-    const float inv_dens = rcp_ftz(v4.w);
+                                              const float4 vi, float4 e4, const float dens, float ax, float ay, float az, const float L,
+                                              const float inv_mass, uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank,
+                                              uint32_t *__restrict__ cell_count) {
+    const bool fixed = __float_as_int(a.O[i].w) != 0;
+    float4 v4 = fixed ? a.VEL[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // a fixed particle keeps its velocity (cpp:603)
+    v4.w = dens;
+    const float inv_dens = rcp_ftz(dens);
     ax *= inv_dens;  // cpp:568
     ay *= inv_dens;
     az *= inv_dens;
     // cpp:571: Inter_Vm += (sigma/(Beta*Cm))*Inter_Vm - ((Iion - stim*dt/mass)/Cm)   (the += form, Q9)
     const float dtm = p.dt * inv_mass;
-    const float ivm = SPHSM_FAST_ODE ? L + (p.diff_coef * L - (e4.y - e4.w * dtm) / p.Cm) : L + (p.diff_coef * L - (e4.y - (e4.w * p.dt) / pi.w) / p.Cm);
+    const float ivm = SPHSM_FAST_ODE ? L + (p.diff_coef * L - (e4.y - e4.w * dtm) / p.Cm) : L + (p.diff_coef * L - (e4.y - div_rn_z(e4.w * p.dt, pi.w)) / p.Cm);
     if (DIAG) a.ACC[i] = make_float4(ax, ay, az, ivm);
-    const bool fixed = __float_as_int(a.O[i].w) != 0;
     float x = pi.x, y = pi.y, z = pi.z;
     integrate_fast(p, fixed, dtm, vi.x, vi.y, vi.z, ax, ay, az, ivm, pi.w, x, y, z, v4.x, v4.y, v4.z, e4.x);
     Pout[i] = make_float4(x, y, z, pi.w);
@@ -281,7 +311,8 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
     const float4 pi = a.P[i];
     const float4 vi = a.V[i];
     float4 e4 = a.E[i];
-    const float pres_i = a.S[i].x;
+    const float2 si = a.S[i];  // (pres, dens)
+    const float pres_i = si.x;
     const float Vm_i = e4.x;
     const float inv_mass = rcp_ftz(pi.w);
     if (SPHSM_FAST_ODE) cell_model_fast(p, e4.x, inv_mass, e4.y, e4.z);
@@ -372,7 +403,7 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
                 lo = lbase;
             });
     }
-    pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, ax, ay, az, L + L1, inv_mass, next_keys, next_rank, cell_count);
+    pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, ax, ay, az, L + L1, inv_mass, next_keys, next_rank, cell_count);
 }
 
 }  // namespace sphsm

@@ -8,7 +8,7 @@
 // reduction.  Same arithmetic per term as sphsm_pass4.cuh (exact r^2 against the same thresholds, so neighbour-set membership
 // is bit-exact); only the order of the floating-point sums differs, within the fast path's 1e-5.
 #pragma once
-#include "sphsm_pass5.cuh"
+#include "sphsm_pass4.cuh"
 
 namespace sphsm {
 
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(PTW) k_pass_b4w(const __grid_constant__ DevPar
     const float4 pi = a.P[i];
     const float4 vi = a.V[i];
     float4 e4 = a.E[i];
-    const float pres_i = a.S[i].x;
+    const float2 si = a.S[i];  // (pres, dens)
+    const float pres_i = si.x;
     const float Vm_i = e4.x;
     const float inv_mass = rcp_ftz(pi.w);
     if (SPHSM_FAST_ODE) cell_model_fast(p, e4.x, inv_mass, e4.y, e4.z);
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(PTW) k_pass_b4w(const __grid_constant__ DevPar
     ay = warp_sum(ay);
     az = warp_sum(az);
     L = warp_sum(L);
-    if (lane == 0) pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, ax, ay, az, L, inv_mass, next_keys, next_rank, cell_count);
+    if (lane == 0) pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, ax, ay, az, L, inv_mass, next_keys, next_rank, cell_count);
 }
 
 }  // namespace sphsm

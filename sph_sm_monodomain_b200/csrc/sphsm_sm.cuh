@@ -480,7 +480,9 @@ __global__ void __launch_bounds__(256) k_reorder_goal(const __grid_constant__ De
     const uint32_t v = vals[s];
     const float4 p4 = src.P[v], v4 = src.VEL[v], o4 = src.O[v], e4 = src.E[v];
     dst.P[s] = p4;
-    dst.VEL[s] = v4;
+    // pass B writes VEL = (vel, dens) of every particle it integrates without reading it (the old velocity is not an input of
+    // cpp:605, the density travels in S); only a FIXED particle keeps its velocity (cpp:603), so only that one is carried over
+    if (__float_as_int(o4.w)) dst.VEL[s] = v4;
     dst.O[s] = o4;
     dst.E[s] = e4;
     dst.ID[s] = src.ID[v];

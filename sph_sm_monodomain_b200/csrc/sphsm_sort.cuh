@@ -393,11 +393,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restric
         }
     }
 }
+// skey[slot] = the key again, in slot order (the in-cell ordering below permutes slots of ONE cell, so it stays valid): the
+// neighbour passes read it instead of recomputing cell coordinates
 __global__ void __launch_bounds__(256) k_cell_scatter(int n, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
-                                                      const int *__restrict__ cell_start, uint32_t *__restrict__ vals) {
+                                                      const int *__restrict__ cell_start, uint32_t *__restrict__ vals, uint32_t *__restrict__ skey) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    vals[(uint32_t)cell_start[keys[i]] + rank[i]] = (uint32_t)i;
+    const uint32_t key = keys[i], slot = (uint32_t)cell_start[key] + rank[i];
+    vals[slot] = (uint32_t)i;
+    skey[slot] = key;
 }
 // in-cell order = ascending ORIGINAL index.  One thread per cell orders cells of up to BIG_CELL particles in place (a lattice
 // holds 1-8 per cell); fuller cells (the reference's meshes reach 75) go on a worklist for k_cell_sort_big — the one-thread

@@ -38,6 +38,12 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
+def tune(name: str, value: int):
+    """sphsm_tune: process-wide kernel-path switch ("pass", "stage6", "t6", "b_step6", "warp_path"); changes no result."""
+    lib = _capi.load()
+    _capi.check(lib, None, lib.sphsm_tune(name.encode(), int(value)))
+
+
 def default_params() -> Params:
     lib = _capi.load()
     p = Params()

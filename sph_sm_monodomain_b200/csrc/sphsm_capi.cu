@@ -104,6 +104,10 @@ struct sphsm_handle {
     int *d_itmp = nullptr;
     size_t itmp_cap = 0;
     bool grid_valid = false, rest_dirty = true, inter_live = true, slot_of_valid = false;
+    // the fast path without diagnostics does not keep GOAL / PV (mGoalPos, predicted_vel) current; a particle that becomes fixed
+    // between steps must still freeze at the values the last step computed for it (cpp:228, 326): see freeze_source()
+    bool goal_pv_stale = false;   // GOAL / PV arrays are older than the last step
+    bool prev_vel_valid = false;  // alt.VEL[vals[sorted_buf][s]] is the velocity slot s had BEFORE the last step
     int sort_passes = 1, max_tiles = 1, red_blocks = 1;
     long long launches = 0;
     int total_steps = 0;
@@ -151,7 +155,7 @@ static const bool g_sync_debug = getenv("SPHSM_SYNC_DEBUG") != nullptr;
 // SPHSM_STAGE6=0 makes every block of the generation-6 kernels take their in-kernel gathered path; SPHSM_T6 = 64 | 128 targets per
 // block; SPHSM_B_STEP6 = 2 | 4 candidates per iteration of pass B's phase 1.
 // The same four switches can be changed at run time with sphsm_tune("pass" | "stage6" | "t6" | "b_step6", value) (tests).
-static int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 6;
+static int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 4;
 static int g_stage6 = getenv("SPHSM_STAGE6") ? atoi(getenv("SPHSM_STAGE6")) : 1;
 static int g_t6 = getenv("SPHSM_T6") ? atoi(getenv("SPHSM_T6")) : 128;
 static int g_b_step6 = getenv("SPHSM_B_STEP6") ? atoi(getenv("SPHSM_B_STEP6")) : 2;
@@ -596,34 +600,63 @@ __global__ void __launch_bounds__(256) k_set_stim_list(int n, Arrays a, const fl
     if (hit && s < n) a.E[s].w = strength;
 }
 
+// What a particle freezes at when it becomes fixed: the mGoalPos / predicted_vel the LAST step computed for it (the reference
+// simply stops updating them, cpp:228, 326).  src 1: the GOAL / PV arrays are current (diagnostics mode, or no fast step since
+// the upload).  src 2: recompute them as the last step did — the shape-matching transform of that step is still in SmState, and
+// the velocity the particle had before that step is still in the gather's source buffer (prev_vel, indexed through the sorted
+// permutation `vals`; nullptr: not available any more, the current velocity stands in).
+struct FreezeSrc {
+    int src, strict;
+    const SmState *sm;
+    const float4 *prev_vel;
+    const uint32_t *vals;
+};
+__device__ __forceinline__ void freeze_goal_pv(const DevParams &p, const Arrays &a, const FreezeSrc &f, int s, int id) {
+    if (f.src == 1) {
+        a.COLD_GOAL[id] = a.GOAL[s];
+        a.COLD_PV[id] = a.PV[s];
+        return;
+    }
+    const float4 p4 = a.P[s], o4 = a.O[s];
+    float4 v4 = f.prev_vel ? f.prev_vel[f.vals[s]] : a.VEL[s];
+    v4.w = 1.0f;
+    const float4 o = make_float4(o4.x, o4.y, o4.z, __int_as_float(0));
+    float4 goal, pv;
+    if (f.strict) goal_cvel_one<true>(p, f.sm, nullptr, nullptr, p4, v4, o, nullptr, goal, pv);
+    else goal_cvel_one<false>(p, f.sm, nullptr, nullptr, p4, v4, o, nullptr, goal, pv);
+    a.COLD_GOAL[id] = goal;
+    a.COLD_PV[id] = pv;
+}
+
 // mode 0: turnOnStim_Mesh's fixation rule (cpp:759), 1: turnOnStim_Cube's (cpp:738); comparisons against double
 // literals are done in double exactly as the reference's promotions make them.
-__global__ void k_fix_rule(int n, Arrays a, int mode, int diag) {
+__global__ void k_fix_rule(const __grid_constant__ DevParams p, int n, Arrays a, int mode, FreezeSrc fz) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const float4 p = a.P[s];
+    const float4 q = a.P[s];
     bool fix;
     if (mode == 0) {
-        const double x = p.x, y = p.y;
+        const double x = q.x, y = q.y;
         fix = (x >= 0.0 && x <= 0.07) || (x >= 0.90 && y >= 0.80);
     } else {
-        fix = (p.y == 0.0f && p.x <= 0.48f) || (p.y == 0.0f && (double)p.x >= 1.0);
+        fix = (q.y == 0.0f && q.x <= 0.48f) || (q.y == 0.0f && (double)q.x >= 1.0);
     }
     if (fix && __float_as_int(a.O[s].w) == 0) {
         const int id = a.ID[s];
-        if (diag) { a.COLD_GOAL[id] = a.GOAL[s]; a.COLD_PV[id] = a.PV[s]; }
+        freeze_goal_pv(p, a, fz, s, id);
         a.O[s].w = __int_as_float(id + 1);
     }
 }
 
-__global__ void k_set_masks(int n, Arrays a, const uint8_t *__restrict__ fixed, const float *__restrict__ stim, int diag) {
+__global__ void k_set_masks(const __grid_constant__ DevParams p, int n, Arrays a, const uint8_t *__restrict__ fixed, const float *__restrict__ stim,
+                            FreezeSrc fz) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int id = a.ID[s];
     if (fixed) {
         const int was = __float_as_int(a.O[s].w);
         if (fixed[id] && !was) {
-            if (diag) { a.COLD_GOAL[id] = a.GOAL[s]; a.COLD_PV[id] = a.PV[s]; }
+            freeze_goal_pv(p, a, fz, s, id);
             a.O[s].w = __int_as_float(id + 1);
         } else if (!fixed[id] && was) {
             a.GOAL[s] = a.COLD_GOAL[was - 1];
@@ -679,10 +712,22 @@ static void state_changed(sphsm_handle *h, bool rest) {
     h->grid_valid = false;
     h->slot_of_valid = false;
     h->inter_live = true;
+    h->prev_vel_valid = false;
     if (rest) {
+        h->goal_pv_stale = false;  // uploads / Init_Fluid write GOAL, PV and their frozen copies
         h->rest_dirty = true;
         h->slab_applied = false;  // the particle set was replaced: sphsm_comm_set_slab must be applied again
     }
+}
+
+static FreezeSrc freeze_source(const sphsm_handle *h) {
+    FreezeSrc f;
+    f.src = (h->prm.diagnostics || !h->goal_pv_stale) ? 1 : 2;
+    f.strict = h->prm.strict;
+    f.sm = h->sm;
+    f.prev_vel = h->prev_vel_valid ? h->alt.VEL : nullptr;
+    f.vals = h->vals[h->sorted_buf];
+    return f;
 }
 
 // Host-side estimate of the mean cell occupancy of a small particle set, from the positions as the caller hands them in
@@ -794,7 +839,7 @@ extern "C" int sphsm_stim_mesh(sphsm_handle *h, const float *xyz, int n) {
     CU(cudaSetDevice(h->prm.device));
     int rc = stim_list(h, xyz, n, 0.01f, h->prm.stim_strength);  // cpp:753
     if (rc) return rc;
-    if (h->n > 0) LAUNCH(k_fix_rule, cdiv(h->n, 256), 256, h->n, h->cur, 0, h->prm.diagnostics);
+    if (h->n > 0) LAUNCH(k_fix_rule, cdiv(h->n, 256), 256, h->dp, h->n, h->cur, 0, freeze_source(h));
     CU(cudaGetLastError());
     h->rest_dirty = true;
     return SPHSM_OK;
@@ -812,7 +857,7 @@ extern "C" int sphsm_stim_cube(sphsm_handle *h, const float *xyz, int n) {
     }
     int rc = stim_list(h, sel.data(), (int)(sel.size() / 3), 0.001f, h->prm.stim_strength);  // cpp:728
     if (rc) return rc;
-    if (h->n > 0) LAUNCH(k_fix_rule, cdiv(h->n, 256), 256, h->n, h->cur, 1, h->prm.diagnostics);
+    if (h->n > 0) LAUNCH(k_fix_rule, cdiv(h->n, 256), 256, h->dp, h->n, h->cur, 1, freeze_source(h));
     CU(cudaGetLastError());
     h->rest_dirty = true;
     return SPHSM_OK;
@@ -837,8 +882,8 @@ extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const floa
     if (stim) CU(cudaMemcpyAsync(h->d_tmp, stim, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     if (fixed) CU(cudaMemcpyAsync(h->d_itmp, fixed, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     if (h->n > 0)
-        LAUNCH(k_set_masks, cdiv(h->n, 256), 256, h->n, h->cur, fixed ? (const uint8_t *)h->d_itmp : nullptr, stim ? h->d_tmp : nullptr,
-               h->prm.diagnostics);
+        LAUNCH(k_set_masks, cdiv(h->n, 256), 256, h->dp, h->n, h->cur, fixed ? (const uint8_t *)h->d_itmp : nullptr, stim ? h->d_tmp : nullptr,
+               freeze_source(h));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     if (fixed) h->rest_dirty = true;

@@ -104,8 +104,8 @@ extern "C" int sphsm_set_masks_async(sphsm_handle *h, const uint8_t *fixed, cons
     CU(cudaEventRecord(h->ev_in_ready, h->h2d_stream));
     CU(cudaStreamWaitEvent(h->stream, h->ev_in_ready, 0));
     if (h->n > 0)
-        LAUNCH(k_set_masks, cdiv(h->n, 256), 256, h->n, h->cur, fixed ? (const uint8_t *)h->io_in_b : nullptr, stim ? h->io_in_f : nullptr,
-               h->prm.diagnostics);
+        LAUNCH(k_set_masks, cdiv(h->n, 256), 256, h->dp, h->n, h->cur, fixed ? (const uint8_t *)h->io_in_b : nullptr, stim ? h->io_in_f : nullptr,
+               freeze_source(h));
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_in_free, h->stream));
     if (fixed) h->rest_dirty = true;

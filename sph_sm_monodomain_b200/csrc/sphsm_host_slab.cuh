@@ -421,6 +421,8 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             CU(cudaGetLastError());
             h->grid_valid = false;
             h->inter_live = false;
+            h->goal_pv_stale = !diag;
+            h->prev_vel_valid = true;
             h->total_steps++;
             *coll = COLL_DONE;
             return SPHSM_OK;

@@ -130,6 +130,7 @@ static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool boun
 
 static int build_grid(sphsm_handle *h, GroupTimer *gt) {
     if (h->n == 0) { h->grid_valid = true; return SPHSM_OK; }
+    h->prev_vel_valid = false;  // a stand-alone re-sort moves every slot: the last step's gather source no longer lines up (freeze_source)
     int rc;
     if ((rc = grid_sort(h, gt)) != 0) return rc;
     return grid_finish(h, gt, 0);
@@ -234,6 +235,8 @@ static int corrected_velocity(sphsm_handle *h, bool diag, GroupTimer *gt, int st
     }
     if (gt) gt->end_group(KG_MOMENTS);
     const int keep_goal = n <= 1;  // projectPositions returned early: mGoalPos keeps its previous value
+    if ((diag || keep_goal) && store == 7) h->goal_pv_stale = false;
+    else if (!(diag || keep_goal)) h->goal_pv_stale = true;
     if (diag || keep_goal) LAUNCH((k_goal_cvel<STRICT, true>), cdiv(n, 256), 256, h->dp, h->cur, h->sm, keep_goal, store);
     else LAUNCH((k_goal_cvel<STRICT, false>), cdiv(n, 256), 256, h->dp, h->cur, h->sm, 0, store);
     if (gt) gt->end_group(KG_GOAL);
@@ -338,7 +341,7 @@ static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, in
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
     if (warp_path(h)) LAUNCH(k_pass_a4w, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->cell_start, count);
-    else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start);
+    else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start, h->key_sorted);
     else if (g_t6 == 64) LAUNCH6(k_pass_a6<64>, 64, false, grid6(begin, end, hole_b, hole_e, 64), d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6);
     else LAUNCH6(k_pass_a6<128>, 128, false, grid6(begin, end, hole_b, hole_e, 128), d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6);
     return SPHSM_OK;
@@ -359,8 +362,8 @@ static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hol
         if (diag) LAUNCH(k_pass_b4w<true>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count);
         else LAUNCH(k_pass_b4w<false>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count);
     } else if (g_pass_gen == 4) {
-        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt);
-        else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt);
+        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt);
+        else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt);
     } else if (g_t6 == 64) {
         const int grid = grid6(begin, end, hole_b, hole_e, 64);
         return g_b_step6 == 4 ? launch_pass_b6<64, 4>(h, d, grid, diag, nk, nr, ncnt) : launch_pass_b6<64, 2>(h, d, grid, diag, nk, nr, ncnt);
@@ -429,6 +432,10 @@ static int fused_step(sphsm_handle *h) {
     gt.finish();
     h->grid_valid = false;
     h->inter_live = false;
+    if (n > 1) {
+        if (!STRICT) h->goal_pv_stale = !diag;  // (the strict path went through corrected_velocity, which set it)
+        h->prev_vel_valid = true;
+    }
     return SPHSM_OK;
 }
 

@@ -99,16 +99,16 @@ __device__ __forceinline__ void load_rows3(const int *__restrict__ mid, int ga, 
 // j+1 (`two` false: j+1 is past the row) and appends the in-range ones at s_list[lofs], lofs += PT; `one(j, lofs)` is the
 // single-candidate form for rows that could overflow the list (dense meshes); `drain(lofs)` consumes the list.
 template <int STEP = 2, class Pair, class One, class Drain>
-__device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict__ cell_start, int ga, int gagb, int key0, int cc, unsigned lbase,
+__device__ __forceinline__ void sweep4(const DevParams &p, const int *__restrict__ cell_start, int ga, int gagb, int key0, unsigned lbase,
                                        unsigned &lofs, Pair &&pair, One &&one, Drain &&drain) {
     const int *center = cell_start + (key0 - 1);
     const unsigned lmax = lbase + LIST_K * LSTEP;
-    const int c_lo = p.c_off, c_hi = p.c_off + p.gcl;
+    // plane validity from the key alone: a lower plane exists iff key >= ga*gb, an upper one iff key + ga*gb < num_cells
     Rows3 cur, nxt;
-    load_rows3(center - gagb, ga, cc - 1 >= c_lo, cur);
+    load_rows3(center - gagb, ga, key0 >= gagb, cur);
 #pragma unroll 1
     for (int dc = -1; dc <= 1; dc++) {
-        if (dc < 1) load_rows3(center + (dc + 1) * gagb, ga, cc + dc + 1 < c_hi, nxt);
+        if (dc < 1) load_rows3(center + (dc + 1) * gagb, ga, dc < 0 || key0 + gagb < p.num_cells, nxt);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             int j = cur.s[k];
@@ -152,7 +152,7 @@ __device__ __forceinline__ void pass_a_finish(const DevParams &p, const Arrays &
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
 __global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
-                                                const int *__restrict__ cell_start) {
+                                                const int *__restrict__ cell_start, const uint32_t *__restrict__ skey) {
     __shared__ int s_list[LIST_K * PT4];
     int i = p.own_begin + blockIdx.x * PT4 + threadIdx.x;
     if (i >= p.hole_begin) i += p.hole_len;
@@ -169,13 +169,13 @@ __global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_consta
     const float nz = -pi.z;
     float dens = 0.0f, pvx = 0.0f, pvy = 0.0f, pvz = 0.0f;
     unsigned lofs = lbase;
-    int ca, cb, cc;
-    if (cell_coords(p, pi.x, pi.y, pi.z, ca, cb, cc)) {
+    const int key = (int)skey[i];  // the sorted cell key of this slot (the limbo bucket = num_cells: no cell, no neighbours)
+    if (key < p.num_cells) {
         auto r2_of = [&](const float4 pj) { return dist2_packed(__fadd2_rn(make_float2(pj.x, pj.y), nxy), pj.z + nz); };
         // four candidates per iteration: a lattice row (3-4 candidates) has all its loads in flight at once — the pair loop
         // left the kernel waiting on L1 (long-scoreboard 9 warps per issue at 87 % L1 data-path utilisation, ncu r01_v7)
         sweep4<4>(
-            p, cell_start, ga, gagb, cell_key(p, ca, cb, cc), cc, lbase, lofs,
+            p, cell_start, ga, gagb, key, lbase, lofs,
             [&](int j, int e, unsigned &lo) {
                 const float4 p0 = __ldg(P + j), p1 = __ldg(P + j + 1), p2 = __ldg(P + j + 2), p3 = __ldg(P + j + 3);
                 const float r0 = r2_of(p0), r1 = r2_of(p1), r2 = r2_of(p2), r3 = r2_of(p3);
@@ -266,10 +266,9 @@ __device__ __forceinline__ void integrate_fast(const DevParams &p, bool fixed, f
 // (cpp:605: vel = inter_vel + acc * dt / mass), so VEL is written here without having been read.
 template <bool DIAG>
 __device__ __forceinline__ void pass_b_finish(const DevParams &p, const Arrays &a, float4 *__restrict__ Pout, const int i, const float4 pi,
-                                              const float4 vi, float4 e4, const float dens, float ax, float ay, float az, const float L,
-                                              const float inv_mass, uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank,
-                                              uint32_t *__restrict__ cell_count) {
-    const bool fixed = __float_as_int(a.O[i].w) != 0;
+                                              const float4 vi, float4 e4, const float dens, const bool fixed, float ax, float ay, float az,
+                                              const float L, const float inv_mass, uint32_t *__restrict__ next_keys,
+                                              uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count) {
     float4 v4 = fixed ? a.VEL[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // a fixed particle keeps its velocity (cpp:603)
     v4.w = dens;
     const float inv_dens = rcp_ftz(dens);
@@ -302,8 +301,8 @@ __device__ __forceinline__ void pass_b_finish(const DevParams &p, const Arrays &
 // rank in the cell, per-cell count — what k_cell_count does, without re-reading the positions)
 template <bool DIAG>
 __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
-                                                float4 *__restrict__ Pout, const int *__restrict__ cell_start, uint32_t *__restrict__ next_keys,
-                                                uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count) {
+                                                float4 *__restrict__ Pout, const int *__restrict__ cell_start, const uint32_t *__restrict__ skey,
+                                                uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count) {
     __shared__ int s_list[LIST_K * PT4];
     int i = p.own_begin + blockIdx.x * PT4 + threadIdx.x;
     if (i >= p.hole_begin) i += p.hole_len;
@@ -312,6 +311,7 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
     const float4 vi = a.V[i];
     float4 e4 = a.E[i];
     const float2 si = a.S[i];  // (pres, dens)
+    const bool fixed = __float_as_int(a.O[i].w) != 0;  // (loaded with the other records: the epilogue does not wait for it)
     const float pres_i = si.x;
     const float Vm_i = e4.x;
     const float inv_mass = rcp_ftz(pi.w);
@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
     const float2 nxy = make_float2(-pi.x, -pi.y), nzv = make_float2(-pi.z, -Vm_i);
     float ax = 0.0f, ay = 0.0f, az = 0.0f, L = 0.0f, L1 = 0.0f;  // two Laplacian accumulators: the pair's terms are independent
     unsigned lofs = lbase;
-    int ca, cb, cc;
-    if (cell_coords(p, pi.x, pi.y, pi.z, ca, cb, cc)) {
+    const int key = (int)skey[i];  // the sorted cell key of this slot (the limbo bucket = num_cells: no cell, no neighbours)
+    if (key < p.num_cells) {
         // one candidate of phase 1: the 2h-support Laplacian term (cpp:563), and whether it is inside the Spiky / Visco
         // support r <= h (cpp:157,163).  r2 <= 1e-12 (INF, SPH_SM_monodomain.h:24, cpp:546) skips the pair.
         // (x, y) and (z, Vm) of the record are differenced as packed pairs: (dx, dy), (dz, Vm_j - Vm_i).
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
             return on && r2 <= sp2;
         };
         sweep4<SPHSM_B_STEP>(
-            p, cell_start, ga, gagb, cell_key(p, ca, cb, cc), cc, lbase, lofs,
+            p, cell_start, ga, gagb, key, lbase, lofs,
 #if SPHSM_B_STEP == 4
             [&](int j, int e, unsigned &lo) {
                 const float4 p0 = __ldg(PB + j), p1 = __ldg(PB + j + 1), p2 = __ldg(PB + j + 2), p3 = __ldg(PB + j + 3);
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
                 lo = lbase;
             });
     }
-    pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, ax, ay, az, L + L1, inv_mass, next_keys, next_rank, cell_count);
+    pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, fixed, ax, ay, az, L + L1, inv_mass, next_keys, next_rank, cell_count);
 }
 
 }  // namespace sphsm

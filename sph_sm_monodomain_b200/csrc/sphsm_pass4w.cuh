@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(PTW) k_pass_b4w(const __grid_constant__ DevPar
     const float4 vi = a.V[i];
     float4 e4 = a.E[i];
     const float2 si = a.S[i];  // (pres, dens)
+    const bool fixed = __float_as_int(a.O[i].w) != 0;
     const float pres_i = si.x;
     const float Vm_i = e4.x;
     const float inv_mass = rcp_ftz(pi.w);
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(PTW) k_pass_b4w(const __grid_constant__ DevPar
     ay = warp_sum(ay);
     az = warp_sum(az);
     L = warp_sum(L);
-    if (lane == 0) pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, ax, ay, az, L, inv_mass, next_keys, next_rank, cell_count);
+    if (lane == 0) pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, fixed, ax, ay, az, L, inv_mass, next_keys, next_rank, cell_count);
 }
 
 }  // namespace sphsm

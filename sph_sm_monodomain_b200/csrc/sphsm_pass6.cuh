@@ -431,11 +431,13 @@ __global__ void __launch_bounds__(T, 640 / T) k_pass_b6(const __grid_constant__ 
     // the block's own records and the ionic model run while the spans are in flight
     float4 pi = make_float4(0.f, 0.f, 0.f, 1.f), vi = make_float4(0.f, 0.f, 0.f, 0.f), e4 = vi;
     float2 si = make_float2(0.f, 1.f);
+    bool fixed = false;
     if (live) {
         pi = a.P[i];
         vi = a.V[i];
         e4 = a.E[i];
         si = a.S[i];  // (pres, dens)
+        fixed = __float_as_int(a.O[i].w) != 0;
     }
     const float Vm_i = e4.x;
     const float inv_mass = rcp_ftz(pi.w);
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(T, 640 / T) k_pass_b6(const __grid_constant__ 
     } else if (valid) {
         pass_b6_neighbours<T, STEP, false>(g, a, cell_start, key, smem0, pi, vi, Vm_i, si.x, ax, ay, az, Lsum);
     }
-    if (live) pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, ax, ay, az, Lsum, inv_mass, next_keys, next_rank, cell_count);
+    if (live) pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, fixed, ax, ay, az, Lsum, inv_mass, next_keys, next_rank, cell_count);
 }
 
 }  // namespace sphsm

@@ -357,3 +357,92 @@ def test_graph_replay_is_bit_identical(Sim, name):
         assert bits_equal(x, y)
     for f in ("pos", "vel", "dens", "pres", "Vm", "Iion", "w", "stim", "fixed", "orig", "mass"):
         assert bits_equal(a[f], b[f]), f
+
+
+@pytest.mark.parametrize("mode", ["fast", "diagnostics", "strict"])
+def test_midrun_fixation_matches_oracle(Sim, mode, parity_record):
+    """A particle fixed BETWEEN steps freezes at the mGoalPos / predicted_vel the last step computed for it (the reference just
+    stops updating them, cpp:228, 326) — also on the fast path without diagnostics, which does not keep those two arrays: the
+    library recomputes them from the last step's transform and the velocity the particle had before that step."""
+    from tests.test_gpu_parity import TOL, assert_close, make_params
+
+    g, _ = load_golden("cube_4913")
+    pos = g["positions"]
+    ora = CpuSim("port")
+    sim = Sim(diagnostics=(mode != "fast"), strict=(mode == "strict"))
+    for s in (ora, sim):
+        s.Init_Fluid(pos)
+        s.turnOnStim_Cube(pos)
+        s.Animation(4)
+    rng = np.random.default_rng(5)
+    newly = (rng.random(len(pos)) < 0.08) & (g["init.fixed"] == 0)
+    fixed = ((g["init.fixed"] != 0) | newly).astype(np.uint8)
+    ora.set_fields(fixed=fixed)
+    sim.set_masks(fixed, None)
+    params = make_params(g)
+    for step in range(3):
+        ora.Animation(1)
+        sim.Animation(1)
+        got, want = sim.particles(), ora.particles()
+        assert np.array_equal(got["fixed"], want["fixed"])
+        if mode == "strict":
+            for f in ("goal", "predicted_vel", "pos", "vel", "dens", "Vm"):
+                assert bits_equal(got[f], want[f]), (step, f)
+            continue
+        for f in ("goal", "predicted_vel"):  # frozen values of the newly fixed particles
+            err = assert_close(f, got[f][newly], want[f][newly], params, tol=100 * TOL)
+            parity_record("midrun_fixation", f"{mode}/step{step + 1}", f + "(newly fixed)", err, 100 * TOL)
+        for f in ("pos", "dens", "Vm", "corrected_vel", "inter_vel"):
+            tol = (1e-3 if f in ("corrected_vel", "inter_vel") else TOL) * 100
+            err = assert_close(f, got[f], want[f], params, tol=tol)
+            parity_record("midrun_fixation", f"{mode}/step{step + 1}", f, err, tol)
+    assert np.abs(want["predicted_vel"][newly]).max() > 1e-3  # the case is not vacuous: they were moving when they froze
+
+
+@pytest.mark.parametrize("case", ["jitter_lattice", "jitter_lattice_quadratic", "dense_mesh", "sparse_cloud"])
+def test_staged_matches_gathered(Sim, case):
+    """The block-staged neighbour passes (generation 6: stencil spans fetched into shared memory by bulk copies) visit the same
+    candidates in the same order with the same arithmetic as the gathered passes: every field of every particle is BIT-IDENTICAL
+    between the gathered generation 4, the staged kernels at 64 / 128 targets per block and 2 / 4 candidates per iteration, and the
+    staged kernels with staging refused for every block.  Covers blocks that stage (lattice), blocks too full to stage (the
+    reference's dense mesh through the thread-per-particle kernels) and key ranges too long to stage (sparse cloud)."""
+    from sph_sm_monodomain_b200.sim import tune
+
+    quadratic, warp = False, 1
+    if case.startswith("jitter_lattice"):
+        pos, world = inputs.lattice(64, 30, 30, jitter=0.05)
+        fixed, stim = inputs.lattice_masks(pos, 64, 8)
+        fixed, stim = fixed.astype(np.uint8), np.where(stim, np.float32(300), np.float32(0)).astype(np.float32)
+        quadratic = case.endswith("quadratic")
+    elif case == "dense_mesh":
+        g, _ = load_golden("cfg2_5211_wave")
+        pos, world, fixed, stim, warp = g["positions"], (1.5, 1.5, 1.5), g["init.fixed"].astype(np.uint8), g["init.stim"].astype(np.float32), 0
+    else:
+        rng = np.random.default_rng(7)
+        pos = (rng.random((20000, 3), dtype=np.float32) * np.float32(1.45) + np.float32(0.02)).astype(np.float32)
+        world, fixed = (1.5, 1.5, 1.5), np.zeros(20000, np.uint8)
+        stim = np.where(pos[:, 0] < 0.3, np.float32(300), np.float32(0)).astype(np.float32)
+    variants = [dict(**{"pass": 4}), dict(**{"pass": 6}, stage6=1, t6=128, b_step6=2), dict(**{"pass": 6}, stage6=1, t6=64, b_step6=4),
+                dict(**{"pass": 6}, stage6=1, t6=128, b_step6=4), dict(**{"pass": 6}, stage6=0, t6=128, b_step6=2)]
+    ref = None
+    try:
+        tune("warp_path", warp)
+        for v in variants:
+            for k, val in v.items():
+                tune(k, val)
+            s = Sim(capacity=len(pos), world=world, diagnostics=True)
+            s.Init_Fluid(pos)
+            s.set_masks(fixed, stim)
+            if quadratic:
+                s.flip_quadratic()
+            s.Animation(4)
+            p = s.particles()
+            s.close()
+            if ref is None:
+                ref = p
+            else:
+                bad = [f for f in FIELDS if not bits_equal(p[f], ref[f])]
+                assert not bad, (v, bad)
+    finally:
+        for k, val in (("pass", 4), ("stage6", 1), ("t6", 128), ("b_step6", 2), ("warp_path", 1)):
+            tune(k, val)

@@ -106,7 +106,7 @@ def test_neighbor_sets_bit_exact(Sim, name, steps):
 
 @pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_stage_parity_from_identical_state(Sim, name, strict):
+def test_stage_parity_from_identical_state(Sim, name, strict, parity_record):
     """Every stage of step 1, each started from the ORACLE's state just before that stage."""
     g, kw = load_golden(name)
     quadratic = CONFIGS[name]["quadratic"]
@@ -135,6 +135,7 @@ def test_stage_parity_from_identical_state(Sim, name, strict):
                                          f"max rel {rel_err(got[f], want[f]):.3e}")
             else:
                 worst[f] = assert_close(f, got[f], want[f], params, tol=tol)
+                parity_record("stage_parity_from_identical_state", name, f, worst[f], tol)
         # fields a stage must NOT touch stay bit-identical to what was uploaded
         untouched = [f for f in ("orig", "mass", "stim") if f not in STAGE_OUT[st]]
         for f in untouched:
@@ -151,7 +152,7 @@ def whole_step_tol(field, quadratic):
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_fused_step_vs_golden(Sim, name):
+def test_fused_step_vs_golden(Sim, name, parity_record):
     """Whole fused steps (diagnostics on: every Particle field) from the initial state against the golden vectors."""
     sim, g = gpu_from_golden(Sim, name)
     params = make_params(g)
@@ -162,6 +163,7 @@ def test_fused_step_vs_golden(Sim, name):
     for st in range(2, 8):
         for f in STAGE_OUT[st]:
             worst[f] = assert_close(f, got[f], g[f"s1.stage{st}.{f}"], params, tol=whole_step_tol(f, quadratic))
+            parity_record("fused_step_vs_golden(float reference)", name, f, worst[f], whole_step_tol(f, quadratic))
     print(name, "fused step 1 vs golden", {k: f"{v:.2e}" for k, v in worst.items()})
     cps = [int(c) for c in g["checkpoints"] if 1 < c <= 10]
     done = 1
@@ -174,7 +176,7 @@ def test_fused_step_vs_golden(Sim, name):
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_fused_step_vs_double_moment_oracle(Sim, name):
+def test_fused_step_vs_double_moment_oracle(Sim, name, parity_record):
     """One whole fused step against the oracle with double moment accumulation (the oracle of record for the
     summation order at large N, SURVEY.md §7 hard part 3): same tolerance classes as against the float reference."""
     g, kw = load_golden(name)
@@ -190,6 +192,7 @@ def test_fused_step_vs_double_moment_oracle(Sim, name):
     for st in range(2, 8):
         for f in STAGE_OUT[st]:
             worst[f] = assert_close(f, got[f], want[f], params, tol=whole_step_tol(f, quadratic))
+            parity_record("fused_step_vs_double_moment_oracle", name, f, worst[f], whole_step_tol(f, quadratic))
     print(name, "fused step 1 vs double-moment oracle", {k: f"{v:.2e}" for k, v in worst.items()})
 
 
@@ -224,7 +227,7 @@ def test_staged_equals_fused(Sim, name):
 
 # --------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["cfg1_4944", "cfg2_5211", "cube_4913", "cfg2_5211_wave", "lattice_24x10x12"])
-def test_trajectory_deviation_bounded(Sim, name):
+def test_trajectory_deviation_bounded(Sim, name, parity_record):
     """Long runs of the production path (linear shape matching) against the golden checkpoints."""
     sim, g = gpu_from_golden(Sim, name, diagnostics=False)
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_spread.json")) as fh:
@@ -239,6 +242,9 @@ def test_trajectory_deviation_bounded(Sim, name):
         vm_scale = max(1.0, float(np.abs(g[f"step{cp}.Vm"]).max()))
         print(f"{name} step {cp}: |dpos| max {dpos.max():.3e} mean {dpos.mean():.3e} (reference's own spread "
               f"{ref['pos_max']:.3e} / {ref['pos_mean']:.3e}); |dVm| max {dvm.max():.3e} (own spread {ref['vm_max']:.3e})")
+        parity_record("trajectory_deviation", f"{name}/step{cp}", "pos_max", dpos.max(), max(5e-3, 3 * ref["pos_max"]))
+        parity_record("trajectory_deviation", f"{name}/step{cp}", "pos_mean", dpos.mean(), max(2e-4, 3 * ref["pos_mean"]))
+        parity_record("trajectory_deviation", f"{name}/step{cp}", "vm_max", dvm.max(), max(1e-3 * vm_scale, 5 * ref["vm_max"]))
         assert dpos.max() <= max(5e-3, 3 * ref["pos_max"]), (cp, dpos.max())
         assert dpos.mean() <= max(2e-4, 3 * ref["pos_mean"]), (cp, dpos.mean())
         assert dvm.max() <= max(1e-3 * vm_scale, 5 * ref["vm_max"]), (cp, dvm.max())

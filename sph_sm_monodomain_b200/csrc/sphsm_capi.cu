@@ -62,9 +62,7 @@ struct sphsm_handle {
     // error at the end of that step (so all ranks stop after the same step, at most one step late).
     int local_error = 0;
     std::string local_error_msg;
-    double *h_flag = nullptr;              // pinned: the summed error flag of the latest moment allreduce
-    cudaEvent_t ev_flag = nullptr;
-    bool flag_pending = false, peer_error = false, failed = false;
+    bool peer_error = false, failed = false;
     bool reordered = false;                // slab step: the gather was queued before the plane boundaries reached the host
     bool split = false;                    // slab step: exchange 2 in flight on the side stream beside the interior planes
     Arrays cur{}, alt{};
@@ -129,8 +127,19 @@ struct sphsm_handle {
     int send_cap = 0;         // particles per exchange-1 message
     int alloc_n = 0;          // slots allocated per array (capacity + room for two halo messages in slab mode)
     uint8_t *msg_send[2] = {nullptr, nullptr}, *msg_recv[2] = {nullptr, nullptr};  // [0] left neighbour, [1] right neighbour
-    int *d_err = nullptr, *d_meta = nullptr, *h_meta = nullptr;
-    int b2 = 0, b3 = 0;       // start of the 2nd / of the last owned plane (exchange-2 ranges)
+    int *d_err = nullptr;
+    // slot ranges of the slab (SlabMeta, sphsm_comm.cuh): two device copies written alternately by the sort of each step
+    // (meta_cur = the one the latest sort wrote) and a ring of pinned host copies the host reads META_LAG steps late
+    SlabMeta *d_meta[2] = {nullptr, nullptr};
+    int meta_cur = 0;
+    static const int META_RING = 8, META_LAG = 2;
+    int *h_ring = nullptr;                 // META_RING x 8 ints, pinned
+    cudaEvent_t ev_ring[META_RING] = {};
+    long long meta_issued = 0, meta_consumed = 0;  // read-backs queued / applied to the host fields below
+    int n_bound = 0;                       // upper bound of the live slot count the grids of the slab step are sized for
+    int own_bound = 0;                     // likewise for the owned slots
+    int *d_count = nullptr;                // sphsm_download_owned_async: the owned count of the queued gather
+    int b2 = 0, b3 = 0;       // start of the 2nd / of the last owned plane, as of the last applied read-back
     int n_global = 0;         // particles uploaded before sphsm_comm_set_slab filtered them (ids are global)
     int mom_n = 0;            // slab step: extent of the PRE-reorder arrays (old slots + both message regions) the REST-state sums scan
     int mom_begin = 0, mom_end = 0;  // slab step: the slots this rank integrated last step; its share of the per-step moment sums
@@ -184,6 +193,8 @@ extern "C" int sphsm_tune(const char *name, int value) {
             }                                                                                           \
         }                                                                                               \
     } while (0)
+
+static int slab_refresh(sphsm_handle *h);  // sphsm_host_slab.cuh: apply every queued read-back of the slab's slot ranges to the host fields
 
 static int fail(sphsm_handle *h, int code, const char *msg) {
     if (h) h->err = msg; else g_create_error = msg;
@@ -384,9 +395,6 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_meta, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_flag, cudaEventDisableTiming));
-    CU(cudaMallocHost(&h->h_flag, sizeof(double)));
-    *h->h_flag = 0.0;
     CU(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&h->ev_in_ready, &h->ev_in_free, &h->ev_out_ready, &h->ev_out_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
@@ -440,8 +448,9 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
     cudaFree(h->d_itmp);
     for (int k = 0; k < 2; k++) { cudaFree(h->msg_send[k]); cudaFree(h->msg_recv[k]); }
-    cudaFree(h->d_err); cudaFree(h->d_meta);
-    if (h->h_meta) cudaFreeHost(h->h_meta);
+    cudaFree(h->d_err); cudaFree(h->d_meta[0]); cudaFree(h->d_meta[1]); cudaFree(h->d_count);
+    if (h->h_ring) cudaFreeHost(h->h_ring);
+    for (auto &e : h->ev_ring) if (e) cudaEventDestroy(e);
     if (h->nccl_comm_red && h->nccl_comm_red != h->nccl_comm && g_nccl_destroy) g_nccl_destroy(h->nccl_comm_red);
     if (h->nccl_comm && g_nccl_destroy) g_nccl_destroy(h->nccl_comm);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -452,8 +461,6 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     for (auto &gx : h->graphs) cudaGraphExecDestroy(gx.exec);
     h->graphs.clear();
     if (h->ev_meta) cudaEventDestroy(h->ev_meta);
-    if (h->ev_flag) cudaEventDestroy(h->ev_flag);
-    if (h->h_flag) cudaFreeHost(h->h_flag);
     for (cudaEvent_t e : {h->ev_in_ready, h->ev_in_free, h->ev_out_ready, h->ev_out_done})
         if (e) cudaEventDestroy(e);
     if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
@@ -786,9 +793,10 @@ extern "C" int sphsm_download_aos(sphsm_handle *h, void *particles, int n, int s
     // slab mode: n counts GLOBAL particles (the caller's array is indexed by original id); only the particles this rank
     // owns are written, everything else in the caller's array keeps its bytes
     const bool slab = h->dp.slab_on != 0;
+    int rc;
+    if ((rc = slab_refresh(h)) != 0) return rc;
     if (n > (slab ? h->prm.capacity : h->n)) return fail(h, SPHSM_ERR_INVALID, "n exceeds the number of particles");
     CU(cudaSetDevice(h->prm.device));
-    int rc;
     if ((rc = ensure_aos(h, (size_t)std::max(std::max(h->n, n), 1) * stride)) != 0) return rc;
     if (stride != SPHSM_PARTICLE_STRIDE || slab)  // keep the caller's other bytes: round-trip through the device image
         CU(cudaMemcpyAsync(h->d_aos, particles, (size_t)n * stride, cudaMemcpyHostToDevice, h->stream));
@@ -803,9 +811,10 @@ extern "C" int sphsm_download_aos(sphsm_handle *h, void *particles, int n, int s
 extern "C" int sphsm_download_positions(sphsm_handle *h, float *xyz, int n) {
     if (!h || !xyz || n < 0) return SPHSM_ERR_INVALID;
     const bool slab = h->dp.slab_on != 0;  // slab mode: n is the GLOBAL count, only owned particles are written
+    int rc;
+    if ((rc = slab_refresh(h)) != 0) return rc;
     if (n > (slab ? h->prm.capacity : h->n)) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
-    int rc;
     if ((rc = ensure_tmp(h, (size_t)std::max(std::max(h->n, n), 1) * 3)) != 0) return rc;
     if (slab) CU(cudaMemcpyAsync(h->d_tmp, xyz, (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     const int nown = h->dp.own_end - h->dp.own_begin;
@@ -817,8 +826,9 @@ extern "C" int sphsm_download_positions(sphsm_handle *h, float *xyz, int n) {
 }
 
 static int stim_list(sphsm_handle *h, const float *centres, int m, float radius, float strength) {
-    if (m <= 0 || h->n <= 0) return SPHSM_OK;
     int rc;
+    if ((rc = slab_refresh(h)) != 0) return rc;
+    if (m <= 0 || h->n <= 0) return SPHSM_OK;
     if ((rc = ensure_tmp(h, (size_t)m * 3)) != 0) return rc;
     CU(cudaMemcpyAsync(h->d_tmp, centres, (size_t)m * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     LAUNCH(k_set_stim_list, cdiv(h->n, 256), 256, h->n, h->cur, h->d_tmp, m, radius, strength);
@@ -866,6 +876,8 @@ extern "C" int sphsm_stim_cube(sphsm_handle *h, const float *xyz, int n) {
 extern "C" int sphsm_stim_off(sphsm_handle *h) {
     if (!h) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
+    int rc0 = slab_refresh(h);
+    if (rc0) return rc0;
     if (h->n > 0) LAUNCH(k_stim_off, cdiv(h->n, 256), 256, h->n, h->cur);
     CU(cudaGetLastError());
     return SPHSM_OK;
@@ -877,6 +889,7 @@ extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const floa
     if (n == 0 || (!fixed && !stim)) return SPHSM_OK;
     CU(cudaSetDevice(h->prm.device));
     int rc;
+    if ((rc = slab_refresh(h)) != 0) return rc;
     if ((rc = ensure_tmp(h, (size_t)n)) != 0) return rc;
     if ((rc = ensure_itmp(h, (size_t)(n + 3) / 4)) != 0) return rc;
     if (stim) CU(cudaMemcpyAsync(h->d_tmp, stim, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));

@@ -20,6 +20,24 @@
 
 namespace sphsm {
 
+// The slot ranges of a rank (live count, plane boundaries) live in DEVICE memory (SlabMeta, double-buffered: the sort of step
+// t writes one, the kernels of step t+1 that still work on the pre-sort layout read it): every kernel of the slab step takes
+// its ranges from there and its grid from a host-side upper bound, so the host never waits for a step to learn them.
+struct SlabMeta {
+    int n_live;        // live slots after the sort: [left halo | owned planes | right halo]
+    int own_begin;     // first owned slot
+    int b2;            // start of the 2nd owned plane
+    int b3;            // start of the last owned plane
+    int own_end;       // end of the owned slots
+    int err0, err1;    // particles that crossed more than one plane / message overflows and face mismatches, so far
+    int flag;          // sum over ranks of "this rank has an error", as it arrived with this step's moment allreduce
+    int rng_all[4];    // launch ranges {begin, end, hole_begin, hole_len}: every owned slot
+    int rng_int[4];    //   the interior planes [b2, b3)
+    int rng_bnd[4];    //   the two boundary planes: [own_begin, own_end) minus the hole [b2, b3)
+    int bound_viol;    // live slots exceeded the grid bound the host launched with
+    int pad[11];
+};
+
 // one message = [count, pad x3] [P x cap] [VEL x cap] [O x cap] [E x cap] [ID x cap]
 struct MsgView {
     int *count;
@@ -35,6 +53,21 @@ inline MsgView msg_view(uint8_t *base, int cap) {
     v.O = v.VEL + cap;
     v.E = v.O + cap;
     v.ID = reinterpret_cast<int *>(v.E + cap);
+    return v;
+}
+
+// exchange 2 (pass A's records of a boundary plane) reuses the message buffers: [count, pad x3] [V x cap] [S x cap]
+struct Msg2View {
+    int *count;
+    float4 *V;
+    float2 *S;
+};
+inline size_t msg2_bytes(int cap) { return 16 + (size_t)cap * (sizeof(float4) + sizeof(float2)); }
+inline Msg2View msg2_view(uint8_t *base, int cap) {
+    Msg2View v;
+    v.count = reinterpret_cast<int *>(base);
+    v.V = reinterpret_cast<float4 *>(base + 16);
+    v.S = reinterpret_cast<float2 *>(v.V + cap);
     return v;
 }
 
@@ -58,12 +91,12 @@ __device__ __forceinline__ void msg_put(const MsgView &m, int k, const Arrays &a
     m.ID[k] = a.ID[s];
 }
 
-// err[0]: particles that crossed more than one plane in a step; err[1]: message overflow
+// err[0]: particles that crossed more than one plane in a step; err[1]: message overflow / face population mismatch
 __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ DevParams p, Arrays a, int has_left, int has_right, MsgView L,
-                                                     MsgView R, int cap, int *err) {
+                                                     MsgView R, int cap, int *err, const SlabMeta *__restrict__ m) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n) return;
-    if (s < p.own_begin || s >= p.own_end) {  // last step's halo copy: the owner sends a fresh one
+    if (s >= m->n_live) return;
+    if (s < m->own_begin || s >= m->own_end) {  // last step's halo copy: the owner sends a fresh one
         a.P[s].x = __int_as_float(0x7fc00000);
         return;
     }
@@ -82,13 +115,18 @@ __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ Dev
     }
 }
 
-// arrivals -> slots [n0, n0 + 2*cap): left message first; unused slots are dead
-__global__ void __launch_bounds__(256) k_mg_unpack(int n0, Arrays a, int has_left, int has_right, MsgView L, MsgView R, int cap) {
+// arrivals -> slots [n0, n0 + 2*cap), n0 = the live count before this step's exchange: left message first; unused slots are dead.
+// A message whose header count exceeds the capacity was truncated by its sender: the receiver flags it in the same step.
+__global__ void __launch_bounds__(256) k_mg_unpack(const SlabMeta *__restrict__ prev, Arrays a, int has_left, int has_right, MsgView L, MsgView R,
+                                                   int cap, int *err) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 2 * cap) return;
+    const int n0 = prev->n_live;
     const int side = idx >= cap, k = idx - side * cap, slot = n0 + idx;
     const MsgView &m = side ? R : L;
-    const int cnt = (side ? has_right : has_left) ? min(*m.count, cap) : 0;
+    const int sent = (side ? has_right : has_left) ? *m.count : 0;
+    if (k == 0 && sent > cap) atomicAdd(&err[1], 1);
+    const int cnt = min(sent, cap);
     if (k < cnt) {
         a.P[slot] = m.P[k];
         a.VEL[slot] = m.VEL[k];
@@ -111,35 +149,68 @@ __global__ void __launch_bounds__(256) k_mg_filter(const __grid_constant__ DevPa
     if (!slab_owned(p, a.P[s])) a.P[s].x = __int_as_float(0x7fc00000);
 }
 
-// meta[0] live slots, [1] own_begin, [2] start of the 2nd owned plane, [3] start of the last owned plane, [4] own_end,
-// [5] err0, [6] err1, [7] spare
-__global__ void k_mg_meta(const int *__restrict__ cell_start, int num_cells, int plane_cells, int gcl, const int *__restrict__ err, int *meta) {
+// the plane boundaries of the freshly sorted array.  flag_src: where this step's allreduce left the summed error flag (nullptr:
+// none); n_bound: the slot count the host sized this step's grids for.
+__global__ void k_mg_meta(const int *__restrict__ cell_start, int num_cells, int plane_cells, int gcl, const int *__restrict__ err,
+                          const double *__restrict__ flag_src, int n_bound, SlabMeta *m) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    meta[0] = cell_start[num_cells];
-    meta[1] = cell_start[plane_cells];
-    meta[2] = cell_start[plane_cells * 2];
-    meta[3] = cell_start[plane_cells * (gcl - 2)];
-    meta[4] = cell_start[plane_cells * (gcl - 1)];
-    meta[5] = err[0];
-    meta[6] = err[1];
-    meta[7] = 0;
+    const int n = cell_start[num_cells], ob = cell_start[plane_cells], b2 = cell_start[plane_cells * 2];
+    const int b3 = cell_start[plane_cells * (gcl - 2)], oe = cell_start[plane_cells * (gcl - 1)];
+    m->n_live = n; m->own_begin = ob; m->b2 = b2; m->b3 = b3; m->own_end = oe;
+    m->err0 = err[0]; m->err1 = err[1] + (n > n_bound ? 1 : 0);  // (more live slots than the grids were sized for: treated like an overflow)
+    m->flag = flag_src ? (int)*flag_src : 0;
+    m->rng_all[0] = ob; m->rng_all[1] = oe; m->rng_all[2] = 0; m->rng_all[3] = 0;
+    const bool three = b3 > b2;  // at least three populated owned planes: an interior exists
+    m->rng_int[0] = b2; m->rng_int[1] = three ? b3 : b2; m->rng_int[2] = 0; m->rng_int[3] = 0;
+    m->rng_bnd[0] = ob; m->rng_bnd[1] = oe; m->rng_bnd[2] = three ? b2 : 0; m->rng_bnd[3] = three ? b3 - b2 : 0;
+    m->bound_viol = n > n_bound ? 1 : 0;
 }
 
-// exchange 2 carries V = (inter_vel, m/dens) and S; the dense copy of V.w that pass B's phase 1 gathers is rebuilt here for
-// the two halo ranges [0, n_left) and [right_begin, right_begin + n_right)
-__global__ void __launch_bounds__(256) k_mg_halo_vn(int n_left, int right_begin, int n_right, const float4 *__restrict__ V, float *__restrict__ VN) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_left + n_right) return;
-    const int s = k < n_left ? k : right_begin + (k - n_left);
-    VN[s] = V[s].w;
+// exchange 2, sender side: pass A's records (V = inter_vel + m/dens, S = pres + dens) of the first owned plane go to the left
+// neighbour, those of the last owned plane to the right one, with the plane population in the header
+__global__ void __launch_bounds__(256) k_mg_pack2(const SlabMeta *__restrict__ m, Arrays a, int has_left, int has_right, Msg2View L, Msg2View R, int cap) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2 * cap) return;
+    const int side = idx >= cap, k = idx - side * cap;
+    if (side ? !has_right : !has_left) return;
+    const int first = side ? m->b3 : m->own_begin, cnt = side ? m->own_end - m->b3 : m->b2 - m->own_begin;
+    const Msg2View &o = side ? R : L;
+    if (k == 0) *o.count = cnt;
+    if (k < min(cnt, cap)) {
+        o.V[k] = a.V[first + k];
+        o.S[k] = a.S[first + k];
+    }
+}
+// receiver side: the left halo plane is slots [0, own_begin), the right one [own_end, n_live); both sides of a face hold the
+// shared plane in the same (canonical) order.  A population that differs from the sender's is an error (err[1]).
+__global__ void __launch_bounds__(256) k_mg_unpack2(const SlabMeta *__restrict__ m, Arrays a, int has_left, int has_right, Msg2View L, Msg2View R,
+                                                    int cap, int *err) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2 * cap) return;
+    const int side = idx >= cap, k = idx - side * cap;
+    if (side ? !has_right : !has_left) return;
+    const int first = side ? m->own_end : 0, cnt = side ? m->n_live - m->own_end : m->own_begin;
+    const Msg2View &in = side ? R : L;
+    if (k == 0 && *in.count != cnt) atomicAdd(&err[1], 1);
+    if (k < min(cnt, cap)) {
+        const float4 v = in.V[k];
+        a.V[first + k] = v;
+        a.S[first + k] = in.S[k];
+        a.VN[first + k] = v.w;  // the dense copy of V.w that pass B's phase 1 gathers
+    }
 }
 
-__global__ void k_store_double(double *dst, double v) { *dst = v; }
+// the rank's error state as one double for the moment allreduce: every rank learns in the same step that some rank failed
+__global__ void k_store_flag(double *dst, const int *__restrict__ err) { *dst = (err[0] | err[1] | err[2]) ? 1.0 : 0.0; }
 
-// compact (id, xyz) of the owned slots for sphsm_download_owned
-__global__ void __launch_bounds__(256) k_mg_owned_out(int first, int count, Arrays a, int *__restrict__ ids, float *__restrict__ xyz) {
+// compact (id, xyz) of the owned slots for sphsm_download_owned; the range comes from device memory (rng = {begin, end}) and the
+// count is left in *count_out for the asynchronous form
+__global__ void __launch_bounds__(256) k_mg_owned_out(const int *__restrict__ rng, int first_h, int count_h, int cap, Arrays a, int *__restrict__ ids,
+                                                      float *__restrict__ xyz, int *__restrict__ count_out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
+    const int first = rng ? rng[0] : first_h, count = rng ? rng[1] - rng[0] : count_h;
+    if (k == 0 && count_out) *count_out = count;
+    if (k >= count || k >= cap) return;
     const float4 q = a.P[first + k];
     ids[k] = a.ID[first + k];
     xyz[3 * (size_t)k] = q.x;

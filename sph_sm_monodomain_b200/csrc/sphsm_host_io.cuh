@@ -103,8 +103,10 @@ extern "C" int sphsm_set_masks_async(sphsm_handle *h, const uint8_t *fixed, cons
     if (fixed) CU(cudaMemcpyAsync(h->io_in_b, fixed, (size_t)n, cudaMemcpyHostToDevice, h->h2d_stream));
     CU(cudaEventRecord(h->ev_in_ready, h->h2d_stream));
     CU(cudaStreamWaitEvent(h->stream, h->ev_in_ready, 0));
-    if (h->n > 0)
-        LAUNCH(k_set_masks, cdiv(h->n, 256), 256, h->dp, h->n, h->cur, fixed ? (const uint8_t *)h->io_in_b : nullptr, stim ? h->io_in_f : nullptr,
+    // slab mode: h->n may lag the device by a step or two; the grid covers the bound and every live slot has a valid id (dead ones: -1)
+    const int n_k = h->dp.slab_on ? std::max(h->n_bound, h->n) : h->n;
+    if (n_k > 0)
+        LAUNCH(k_set_masks, cdiv(n_k, 256), 256, h->dp, n_k, h->cur, fixed ? (const uint8_t *)h->io_in_b : nullptr, stim ? h->io_in_f : nullptr,
                freeze_source(h));
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_in_free, h->stream));
@@ -138,17 +140,36 @@ extern "C" int sphsm_download_positions_async(sphsm_handle *h, float *xyz, int n
 extern "C" int sphsm_download_owned_async(sphsm_handle *h, int *ids, float *xyz, int cap, int *count) {
     if (!h || !ids || !xyz || !count || cap < 0) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
-    const int first = h->dp.own_begin, nown = h->dp.own_end - h->dp.own_begin;
-    *count = nown;
-    if (nown > cap) return fail(h, SPHSM_ERR_CAPACITY, "output arrays smaller than the number of owned particles");
-    if (nown == 0) return SPHSM_OK;
     int rc;
-    if ((rc = ensure_io_out(h, (size_t)std::max(nown, h->prm.capacity / std::max(h->nranks, 1) + 65536))) != 0) return rc;
-    if ((size_t)nown > h->io_out_cap && (rc = ensure_io_out(h, (size_t)nown)) != 0) return rc;
+    if (!h->dp.slab_on) {  // one GPU: every particle is owned, the count is known
+        const int nown = h->n;
+        *count = nown;
+        if (nown > cap) return fail(h, SPHSM_ERR_CAPACITY, "output arrays smaller than the number of owned particles");
+        if (nown == 0) return SPHSM_OK;
+        if ((rc = ensure_io_out(h, (size_t)nown)) != 0) return rc;
+        CU(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));
+        LAUNCH(k_mg_owned_out, cdiv(nown, 256), 256, (const int *)nullptr, 0, nown, nown, h->cur, h->io_out_i, h->io_out_f, (int *)nullptr);
+        CU(cudaGetLastError());
+        return io_copy_out(h, ids, xyz, (size_t)nown);
+    }
+    // Slab mode: the owned range lives in device memory (the host does not wait for a step to learn it), so the gather covers
+    // the owned-count bound, min(cap, bound) records cross PCIe and the count follows them into *count — valid, like the
+    // arrays, once sphsm_io_wait / sphsm_sync has returned.  More owned particles than `cap`: the surplus is not delivered
+    // and *count says so.
+    const int take = std::min(cap, h->own_bound);
+    if (take <= 0) { *count = 0; return SPHSM_OK; }
+    if ((rc = ensure_io_out(h, (size_t)std::max(take, h->prm.capacity / std::max(h->nranks, 1) + 65536))) != 0) return rc;
+    if ((size_t)take > h->io_out_cap && (rc = ensure_io_out(h, (size_t)take)) != 0) return rc;
     CU(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));
-    LAUNCH(k_mg_owned_out, cdiv(nown, 256), 256, first, nown, h->cur, h->io_out_i, h->io_out_f);
+    LAUNCH(k_mg_owned_out, cdiv(take, 256), 256, h->d_meta[h->meta_cur]->rng_all, 0, 0, take, h->cur, h->io_out_i, h->io_out_f, h->d_count);
     CU(cudaGetLastError());
-    return io_copy_out(h, ids, xyz, (size_t)nown);
+    CU(cudaEventRecord(h->ev_out_ready, h->stream));
+    CU(cudaStreamWaitEvent(h->d2h_stream, h->ev_out_ready, 0));
+    CU(cudaMemcpyAsync(count, h->d_count, sizeof(int), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CU(cudaMemcpyAsync(ids, h->io_out_i, (size_t)take * sizeof(int), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CU(cudaMemcpyAsync(xyz, h->io_out_f, (size_t)take * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->d2h_stream));
+    CU(cudaEventRecord(h->ev_out_done, h->d2h_stream));
+    return SPHSM_OK;
 }
 
 extern "C" int sphsm_io_wait(sphsm_handle *h) {

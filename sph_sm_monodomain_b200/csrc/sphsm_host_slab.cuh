@@ -67,8 +67,13 @@ static int comm_alloc(sphsm_handle *h) {
     }
     CU(cudaMalloc(&h->d_err, 4 * sizeof(int)));
     CU(cudaMemset(h->d_err, 0, 4 * sizeof(int)));
-    CU(cudaMalloc(&h->d_meta, 8 * sizeof(int)));
-    CU(cudaMallocHost(&h->h_meta, 8 * sizeof(int)));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaMalloc(&h->d_meta[k], sizeof(SlabMeta)));
+        CU(cudaMemset(h->d_meta[k], 0, sizeof(SlabMeta)));
+    }
+    CU(cudaMalloc(&h->d_count, sizeof(int)));
+    CU(cudaMallocHost(&h->h_ring, sphsm_handle::META_RING * 8 * sizeof(int)));
+    for (auto &e : h->ev_ring) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return SPHSM_OK;
 }
 
@@ -118,49 +123,71 @@ extern "C" int sphsm_comm_init_local(sphsm_handle **hs, int nranks) {
     return SPHSM_OK;
 }
 
-// read the plane boundaries back (one 32-byte copy + stream sync) and set n / owned range from them
+// ---- the slot ranges of the slab: written on the device by every sort, read back by the host with a fixed lag --------------
+// The kernels of the slab step take their ranges from SlabMeta in device memory and their grids from the bounds below, so the
+// host only needs the numbers for (a) those bounds, (b) the accessors, (c) the error state.  Each sort queues a 32-byte copy of
+// the fresh SlabMeta into a ring of pinned slots; the NCCL step applies the copy of step t - META_LAG at the start of step t
+// (an event wait that has normally completed long before), which keeps the host up to META_LAG steps ahead of the device while
+// every rank still sees a given step's error flag at the SAME step (the lag is fixed, not "whatever has arrived").
 static bool g_host_prof_early() { static const bool v = getenv("SPHSM_HOST_PROF") != nullptr; return v; }
 static double now_us_early() {
     timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
-static int slab_meta_launch(sphsm_handle *h) {
+// queue k_mg_meta for the freshly sorted array (it becomes d_meta[meta_cur]) and its read-back
+static int slab_meta_launch(sphsm_handle *h, const double *flag_src) {
     const DevParams &d = h->dp;
-    LAUNCH(k_mg_meta, 1, 32, h->cell_start, d.num_cells, d.ga * d.gb, d.gcl, h->d_err, h->d_meta);
-    CU(cudaMemcpyAsync(h->h_meta, h->d_meta, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaEventRecord(h->ev_meta, h->stream));
+    if (h->meta_issued - h->meta_consumed >= sphsm_handle::META_RING) return fail(h, SPHSM_ERR_COMM, "internal: slab read-back ring overrun");
+    h->meta_cur ^= 1;
+    LAUNCH(k_mg_meta, 1, 32, h->cell_start, d.num_cells, d.ga * d.gb, d.gcl, h->d_err, flag_src, h->n_bound, h->d_meta[h->meta_cur]);
+    const int slot = (int)(h->meta_issued % sphsm_handle::META_RING);
+    CU(cudaMemcpyAsync(h->h_ring + 8 * slot, h->d_meta[h->meta_cur], 8 * sizeof(int), cudaMemcpyDeviceToHost, h->launch_stream));
+    CU(cudaEventRecord(h->ev_ring[slot], h->launch_stream));
+    h->meta_issued++;
     return SPHSM_OK;
 }
-static int slab_meta_read(sphsm_handle *h) {
-    const double tw = g_host_prof_early() ? now_us_early() : 0.0;
-    CU(cudaEventSynchronize(h->ev_meta));  // (not the stream: work queued behind the read-back keeps running)
-    if (tw != 0.0) h->meta_wait_us += now_us_early() - tw;
-    const int *m = h->h_meta;
-    const char *what = m[5] ? "a particle crossed more than one cell plane in one step (or left the slab window)"
-                       : m[6] ? "halo message overflow: raise params.reserved[0] (halo capacity)" : nullptr;
-    const bool defer = h->comm_mode == 1 && h->nranks > 1 && h->slab_applied;  // inside an NCCL step: see local_error
-    if (what && !defer) return fail(h, SPHSM_ERR_COMM, what);
-    if (what && !h->local_error) {
-        h->local_error = 1;
-        h->local_error_msg = what;
+static void slab_set_bounds(sphsm_handle *h, int n_live, int n_owned) {
+    // a step changes the populations by at most the contents of two halo messages; the grids are sized for a few steps of that
+    const int slack = 2 * h->send_cap + 4096;
+    h->n_bound = std::min(h->alloc_n - 2 * h->send_cap, n_live + slack);
+    h->own_bound = std::min(h->alloc_n - 2 * h->send_cap, n_owned + slack);
+}
+// apply the read-backs up to and including number `upto` (0-based count of sorts) to the host-side fields; blocks until they are there
+static int slab_meta_consume(sphsm_handle *h, long long upto) {
+    upto = std::min(upto, h->meta_issued - 1);
+    while (h->meta_consumed <= upto) {
+        const int slot = (int)(h->meta_consumed % sphsm_handle::META_RING);
+        const double tw = g_host_prof_early() ? now_us_early() : 0.0;
+        CU(cudaEventSynchronize(h->ev_ring[slot]));
+        if (tw != 0.0) h->meta_wait_us += now_us_early() - tw;
+        const int *m = h->h_ring + 8 * slot;
+        h->meta_consumed++;
+        h->n = m[0];
+        h->dp.n = m[0];
+        h->dp.own_begin = m[1];
+        h->b2 = m[2];
+        h->b3 = m[3];
+        h->dp.own_end = m[4];
+        slab_set_bounds(h, m[0], m[4] - m[1]);
+        const char *what = m[5] ? "a particle crossed more than one cell plane in one step (or left the slab window)"
+                           : m[6] ? "halo message overflow or a slab face whose two sides disagree: raise params.reserved[0] (halo capacity)" : nullptr;
+        if (what && !h->local_error) {
+            h->local_error = 1;
+            h->local_error_msg = what;
+        }
+        if (m[7] != 0) h->peer_error = true;  // the allreduced flag: some rank (maybe this one) has failed
     }
-    if (defer && h->flag_pending) {
-        CU(cudaEventSynchronize(h->ev_flag));
-        h->flag_pending = false;
-        if (*h->h_flag != 0.0) h->peer_error = true;
-    }
-    h->n = m[0];
-    h->dp.n = m[0];
-    h->dp.own_begin = m[1];
-    h->b2 = m[2];
-    h->b3 = m[3];
-    h->dp.own_end = m[4];
     return SPHSM_OK;
 }
-static int slab_meta(sphsm_handle *h) {
-    int rc = slab_meta_launch(h);
-    return rc ? rc : slab_meta_read(h);
+// everything queued so far, now (accessors, mutators, virtual ranks): the host fields are exact afterwards
+static int slab_refresh(sphsm_handle *h) {
+    if (!h->dp.slab_on || h->meta_consumed >= h->meta_issued) return SPHSM_OK;
+    return slab_meta_consume(h, h->meta_issued - 1);
+}
+static int slab_check_local_error(sphsm_handle *h) {
+    if (h->local_error) return fail(h, SPHSM_ERR_COMM, h->local_error_msg.c_str());
+    return SPHSM_OK;
 }
 
 extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
@@ -177,22 +204,29 @@ extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
     int rc;
     if ((rc = setup_grid_buffers(h)) != 0) return rc;
     // keep only the owned planes: dead entries sort into the limbo bucket and fall off the end
+    h->local_error = 0; h->peer_error = false; h->failed = false;
+    h->meta_consumed = h->meta_issued;  // (read-backs of an earlier slab are void)
+    if (h->d_err) CU(cudaMemsetAsync(h->d_err, 0, 4 * sizeof(int), h->stream));
+    h->n_bound = h->alloc_n;
     if (h->n > 0) {
         d.own_begin = 0; d.own_end = h->n;
         LAUNCH(k_mg_filter, cdiv(h->n, 256), 256, h->dp, h->cur);
         h->inter_live = true;
         if ((rc = build_grid(h, nullptr)) != 0) return rc;
-        if ((rc = slab_meta(h)) != 0) return rc;
+        if ((rc = slab_meta_launch(h, nullptr)) != 0 || (rc = slab_refresh(h)) != 0 || (rc = slab_check_local_error(h)) != 0) return rc;
+    } else {
+        CU(cudaMemsetAsync(h->d_meta[h->meta_cur], 0, sizeof(SlabMeta), h->stream));
+        slab_set_bounds(h, 0, 0);
     }
     h->grid_valid = false;
     h->slab_applied = true;
-    h->local_error = 0; h->peer_error = false; h->failed = false; h->flag_pending = false;
-    if (h->d_err) CU(cudaMemsetAsync(h->d_err, 0, 4 * sizeof(int), h->stream));
     return SPHSM_OK;
 }
 
 extern "C" int sphsm_comm_info(sphsm_handle *h, int out[8]) {
     if (!h || !out) return SPHSM_ERR_INVALID;
+    int rc0 = slab_refresh(h);
+    if (rc0) return rc0;
     out[0] = h->comm_mode; out[1] = h->nranks; out[2] = h->rank; out[3] = h->n;
     out[4] = h->dp.own_begin; out[5] = h->dp.own_end; out[6] = h->send_cap; out[7] = h->dp.slab_on;
     return SPHSM_OK;
@@ -201,13 +235,14 @@ extern "C" int sphsm_comm_info(sphsm_handle *h, int out[8]) {
 extern "C" int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int cap, int *count) {
     if (!h || !ids || !xyz || !count || cap < 0) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if ((rc = slab_refresh(h)) != 0) return rc;
     const int first = h->dp.own_begin, nown = h->dp.own_end - h->dp.own_begin;
     *count = nown;
     if (nown > cap) return fail(h, SPHSM_ERR_CAPACITY, "output arrays smaller than the number of owned particles");
     if (nown == 0) return SPHSM_OK;
-    int rc;
     if ((rc = ensure_tmp(h, (size_t)nown * 3)) != 0 || (rc = ensure_itmp(h, (size_t)nown)) != 0) return rc;
-    LAUNCH(k_mg_owned_out, cdiv(nown, 256), 256, first, nown, h->cur, h->d_itmp, h->d_tmp);
+    LAUNCH(k_mg_owned_out, cdiv(nown, 256), 256, (const int *)nullptr, first, nown, nown, h->cur, h->d_itmp, h->d_tmp, (int *)nullptr);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(ids, h->d_itmp, (size_t)nown * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(xyz, h->d_tmp, (size_t)nown * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -235,31 +270,33 @@ static int nccl_exchange1(sphsm_handle *h) {
     NC(g_nccl.GroupEnd());
     return SPHSM_OK;
 }
-// boundary planes' pass-A results: V = (inter_vel, m/dens) and S = (pres, Vm), contiguous slot ranges on both sides
+// exchange 2: pass A's records of the two boundary planes, packed by k_mg_pack2 into the (free by now) message buffers.  The
+// messages have a fixed size like those of exchange 1 — the plane populations are only known on the device — and carry the
+// population in their header; the receiver (k_mg_unpack2) checks it against its own halo plane.
 static int nccl_exchange2(sphsm_handle *h, cudaStream_t st) {
-    const int ob = h->dp.own_begin, oe = h->dp.own_end, n = h->n;
+    const size_t bytes = msg2_bytes(h->send_cap);
     NC(g_nccl.GroupStart());
     if (h->rank > 0) {
-        NC(g_nccl.Send(h->cur.V + ob, (size_t)(h->b2 - ob) * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
-        NC(g_nccl.Send(h->cur.S + ob, (size_t)(h->b2 - ob) * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
-        NC(g_nccl.Recv(h->cur.V, (size_t)ob * 4, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
-        NC(g_nccl.Recv(h->cur.S, (size_t)ob * 2, NCCL_FLOAT, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->msg_send[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->msg_recv[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, st));
     }
     if (h->rank < h->nranks - 1) {
-        NC(g_nccl.Send(h->cur.V + h->b3, (size_t)(oe - h->b3) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
-        NC(g_nccl.Send(h->cur.S + h->b3, (size_t)(oe - h->b3) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
-        NC(g_nccl.Recv(h->cur.V + oe, (size_t)(n - oe) * 4, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
-        NC(g_nccl.Recv(h->cur.S + oe, (size_t)(n - oe) * 2, NCCL_FLOAT, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->msg_send[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->msg_recv[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, st));
     }
     NC(g_nccl.GroupEnd());
-    const int halo = ob + (n - oe);  // VN (the dense copy of V.w) of the halo slots is rebuilt locally
-    if (halo > 0) {
-        cudaStream_t keep = h->launch_stream;
-        h->launch_stream = st;
-        int rc = [&]() -> int { LAUNCH(k_mg_halo_vn, cdiv(halo, 256), 256, ob, oe, n - oe, h->cur.V, h->cur.VN); return SPHSM_OK; }();
-        h->launch_stream = keep;
-        if (rc) return rc;
-    }
+    return SPHSM_OK;
+}
+static int pack2(sphsm_handle *h) {
+    const int cap = h->send_cap;
+    LAUNCH(k_mg_pack2, cdiv(2 * cap, 256), 256, h->d_meta[h->meta_cur], h->cur, h->rank > 0 ? 1 : 0, h->rank < h->nranks - 1 ? 1 : 0,
+           msg2_view(h->msg_send[0], cap), msg2_view(h->msg_send[1], cap), cap);
+    return SPHSM_OK;
+}
+static int unpack2(sphsm_handle *h) {
+    const int cap = h->send_cap;
+    LAUNCH(k_mg_unpack2, cdiv(2 * cap, 256), 256, h->d_meta[h->meta_cur], h->cur, h->rank > 0 ? 1 : 0, h->rank < h->nranks - 1 ? 1 : 0,
+           msg2_view(h->msg_recv[0], cap), msg2_view(h->msg_recv[1], cap), cap, h->d_err);
     return SPHSM_OK;
 }
 
@@ -268,16 +305,25 @@ enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE, COLL_AL
 static const int MG_PHASES = 6;
 
 static int mg_forked_allreduce(sphsm_handle *h);
+// `sync_meta`: the host waits for the plane boundaries in every step (virtual ranks, profiling, the first step after the
+// rest state changed: its sums need host-side extents); otherwise it runs ahead (slab_meta_consume with the fixed lag)
+static bool mg_sync_meta(const sphsm_handle *h) { return h->comm_mode != 1 || h->nranks == 1 || h->profiling || h->rest_dirty; }
+
 static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
     const bool diag = h->prm.diagnostics != 0;
     const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
+    const int cap = h->send_cap;
     int rc;
     *coll = COLL_NONE; *count = 0;
     switch (phase) {
         case 0: {  // classify + pack
             if (h->profiling) h->gt = new GroupTimer(h);
-            h->mom_begin = h->dp.own_begin;
-            h->mom_end = h->dp.own_end;
+            if (mg_sync_meta(h)) {
+                if ((rc = slab_refresh(h)) != 0) return rc;
+            } else if ((rc = slab_meta_consume(h, h->meta_issued - 1 - sphsm_handle::META_LAG)) != 0) return rc;
+            if (h->comm_mode != 1 || h->nranks == 1) {
+                if ((rc = slab_check_local_error(h)) != 0) return rc;  // (NCCL ranks stop together, through the allreduced flag)
+            }
             h->moments_forked = false;
             if (h->comm_mode == 1 && !h->rest_dirty && !h->profiling) {
                 // the moment sums, their allreduce and the solve only need last step's owned slots: they run on the side
@@ -299,48 +345,39 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             }
             CU(cudaMemsetAsync(h->msg_send[0], 0, 16, h->stream));
             CU(cudaMemsetAsync(h->msg_send[1], 0, 16, h->stream));
-            if (h->n > 0)
-                LAUNCH(k_mg_classify, cdiv(h->n, 256), 256, h->dp, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_send[0], h->send_cap),
-                       msg_view(h->msg_send[1], h->send_cap), h->send_cap, h->d_err);
+            LAUNCH(k_mg_classify, cdiv(std::max(h->n_bound, 1), 256), 256, h->dp, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_send[0], cap),
+                   msg_view(h->msg_send[1], cap), cap, h->d_err, h->d_meta[h->meta_cur]);
             if (h->gt) h->gt->end_group(KG_OTHER);
             *coll = COLL_EXCH1;
             return SPHSM_OK;
         }
         case 1: {  // unpack arrivals, hash + sort everything, cell table, plane boundaries
-            const int n0 = h->n, cap = h->send_cap;
-            if (n0 + 2 * cap > h->alloc_n) return fail(h, SPHSM_ERR_CAPACITY, "capacity too small for the halo arrivals");
-            LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, n0, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_recv[0], cap),
-                   msg_view(h->msg_recv[1], cap), cap);
-            h->n = n0 + 2 * cap;
-            h->dp.n = h->n;
-            h->mom_n = h->n;
+            if (h->n_bound + 2 * cap > h->alloc_n) return fail(h, SPHSM_ERR_CAPACITY, "capacity too small for the halo arrivals");
+            const SlabMeta *prev = h->d_meta[h->meta_cur];
+            LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, prev, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_recv[0], cap),
+                   msg_view(h->msg_recv[1], cap), cap, h->d_err);
+            // the entries to sort are the previous live slots + both message regions; the kernels read that count from `prev`,
+            // the grids are sized for its upper bound.  (h->n itself is the host's last applied read-back: exact whenever the
+            // host waits for the boundaries, i.e. in every step whose rest-state sums need the extent below.)
+            h->mom_n = h->n + 2 * cap;
             if (h->gt) h->gt->end_group(KG_OTHER);
-            if ((rc = grid_sort(h, h->gt)) != 0) return rc;
-            if (!h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(h->n + 1, 256), 256, h->keys[h->sorted_buf], h->cell_start, h->n, h->dp.num_cells);
+            if ((rc = grid_sort(h, h->gt, &prev->n_live, 2 * cap, h->n_bound + 2 * cap)) != 0) return rc;
             h->reordered = false;
-            if (h->moments_forked && h->bounds_ready) {
-                // the gather needs the live count only as a bound: it is queued behind the read-back with the count taken
-                // from device memory, so the GPU is busy while the host waits for the plane boundaries
-                if ((rc = slab_meta_launch(h)) != 0) return rc;
+            const int nacc = h->dp.quadratic ? 33 : 15;
+            if (h->moments_forked) {
+                // the forked chain has delivered the transform and the summed error flag: plane boundaries + flag -> SlabMeta,
+                // then the gather, which takes the live count from there
                 CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
                 h->moments_forked = false;
-                if ((rc = grid_finish(h, h->gt, diag ? 2 : 1, true, h->d_meta)) != 0) return rc;
+                if ((rc = slab_meta_launch(h, h->totals + nacc)) != 0) return rc;
+                if ((rc = grid_finish(h, h->gt, diag ? 2 : 1, true, &h->d_meta[h->meta_cur]->n_live, h->n_bound + 2 * cap)) != 0) return rc;
                 h->reordered = true;
-                if ((rc = slab_meta_read(h)) != 0) return rc;
-            } else if ((rc = slab_meta(h)) != 0) return rc;  // n = live slots from here on
-            if (!h->bounds_ready && !h->prm.reserved[1] && h->n > 0) {  // (the counting sort leaves every cell in canonical order)
-                // canonical in-cell order (ascending original id) where two ranks must agree slot by slot: the halo
-                // plane and the owned plane on either side of each face (arrivals were appended in atomic order)
-                const int src = h->sorted_buf, ob = h->dp.own_begin, oe = h->dp.own_end;
-                const bool one = h->b3 <= h->b2;  // slab of one or two planes: the ranges meet
-                const int r0 = 0, c0 = one ? h->n : (has_left ? h->b2 : 0);
-                const int r1 = h->b3, c1 = one ? 0 : (has_right ? h->n - h->b3 : 0);
-                (void)ob; (void)oe;
-                if (c0 > 0) LAUNCH(k_cell_order_fix, cdiv(c0, 128), 128, h->keys[src], h->vals[src], h->cur.ID, h->n, (uint32_t)h->dp.num_cells, r0, c0);
-                if (c1 > 0) LAUNCH(k_cell_order_fix, cdiv(c1, 128), 128, h->keys[src], h->vals[src], h->cur.ID, h->n, (uint32_t)h->dp.num_cells, r1, c1);
+            } else {
+                if ((rc = slab_meta_launch(h, nullptr)) != 0) return rc;
+                if ((rc = slab_refresh(h)) != 0) return rc;  // n = live slots from here on (host-side extents for the sums below)
             }
             if (h->gt) h->gt->end_group(KG_GRID);
-            if (h->rest_dirty) {
+            if (h->rest_dirty) {  // (the sums scan the PRE-gather arrays: old slots + both message regions, mom_n entries)
                 if ((rc = rest_part1(h)) != 0) return rc;
                 *coll = COLL_ALLREDUCE; *count = 5;
             }
@@ -353,9 +390,13 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             }
             return SPHSM_OK;
         case 3:
-            if (h->moments_forked || h->reordered) return SPHSM_OK;
+            if (h->reordered) return SPHSM_OK;
             if (h->rest_dirty && (rc = rest_part3(h)) != 0) return rc;
-            if ((rc = moments_part(h)) != 0) return rc;
+            // (not forked: the per-step sums run here, over the PREVIOUS layout's owned range, which the arrays still have)
+            h->meta_cur ^= 1;
+            rc = moments_part(h);
+            h->meta_cur ^= 1;
+            if (rc) return rc;
             *coll = COLL_ALLREDUCE_MOMENTS; *count = h->dp.quadratic ? 33 : 15;
             return SPHSM_OK;
         case 4: {  // solve, gather + stage 2, pass A
@@ -363,17 +404,19 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 h->dp_uploaded = h->dp;
                 CU(cudaMemcpyAsync(h->d_dp, &h->dp_uploaded, sizeof(DevParams), cudaMemcpyHostToDevice, h->stream));
             }
-            if (h->reordered) {
-            } else if (h->moments_forked) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-            else LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
-            h->moments_forked = false;
-            h->mom_n = 0;
-            if (h->gt) h->gt->end_group(KG_MOMENTS);
-            if (h->n > 0 && !h->reordered && (rc = grid_finish(h, h->gt, diag ? 2 : 1, true)) != 0) return rc;
-            const int ob = h->dp.own_begin, oe = h->dp.own_end;
+            const SlabMeta *m = h->d_meta[h->meta_cur];
+            if (!h->reordered) {
+                LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm);
+                h->mom_n = 0;
+                if (h->gt) h->gt->end_group(KG_MOMENTS);
+                if ((rc = grid_finish(h, h->gt, diag ? 2 : 1, true, &m->n_live, h->n_bound + 2 * cap)) != 0) return rc;
+            } else {
+                h->mom_n = 0;
+                if (h->gt) h->gt->end_group(KG_MOMENTS);
+            }
             // NCCL mode with at least three owned planes: pass A on the two boundary planes first, their V / S records travel
             // on the side stream while the interior planes are computed here (and pass B's interior after them)
-            h->split = h->comm_mode == 1 && h->nranks > 1 && !h->profiling && h->b2 < h->b3;
+            h->split = h->comm_mode == 1 && h->nranks > 1 && !h->profiling && h->dp.slab_hi - h->dp.slab_lo >= 3;
             if (h->split) {
                 // side stream (high priority): pass A on the two boundary planes -> exchange 2 -> pass B on them;
                 // main stream: pass A, then pass B on the interior planes.  Cross dependencies: pass B's interior reads the
@@ -381,36 +424,42 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 CU(cudaEventRecord(h->ev_fork, h->stream));
                 CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
                 h->launch_stream = h->side_stream;
-                rc = launch_pass_a(h, ob, oe, h->b2, h->b3);
+                rc = launch_pass_a(h, 0, 2 * cap, 0, 0, m->rng_bnd);
+                if (!rc) rc = pack2(h);
                 h->launch_stream = h->stream;
                 if (rc) return rc;
                 CU(cudaEventRecord(h->ev_bnd, h->side_stream));
-                if ((rc = launch_pass_a(h, h->b2, h->b3)) != 0) return rc;  // (queued before the NCCL calls: they take host time)
+                if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_int)) != 0) return rc;  // (queued before the NCCL calls: they take host time)
                 CU(cudaEventRecord(h->ev_int, h->stream));
                 CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
-                if ((rc = launch_pass_b(h, h->b2, h->b3, diag)) != 0) return rc;
+                if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_int)) != 0) return rc;
                 if (g_host_prof_early() && h->pev[4]) CU(cudaEventRecord(h->pev[4], h->side_stream));
                 rc = nccl_exchange2(h, h->side_stream);
                 if (g_host_prof_early() && h->pev[5]) CU(cudaEventRecord(h->pev[5], h->side_stream));
                 return rc;
             }
-            if ((rc = launch_pass_a(h, ob, oe)) != 0) return rc;
+            if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_all)) != 0) return rc;
+            if ((rc = pack2(h)) != 0) return rc;
             if (h->gt) h->gt->end_group(KG_PASS_A);
             *coll = COLL_EXCH2;
             return SPHSM_OK;
         }
         case 5: {  // pass B on the owned slots
             if (h->gt) h->gt->end_group(KG_OTHER);  // exchange 2
-            const int ob = h->dp.own_begin, oe = h->dp.own_end;
+            const SlabMeta *m = h->d_meta[h->meta_cur];
             if (h->split) {  // interior planes need no halo record; the boundary planes wait for exchange 2 (stream order)
                 CU(cudaStreamWaitEvent(h->side_stream, h->ev_int, 0));  // (pass B's interior was queued in phase 4)
                 h->launch_stream = h->side_stream;
-                rc = launch_pass_b(h, ob, oe, diag, h->b2, h->b3);
+                rc = unpack2(h);
+                if (!rc) rc = launch_pass_b(h, 0, 2 * cap, diag, 0, 0, false, m->rng_bnd);
                 h->launch_stream = h->stream;
                 if (rc) return rc;
                 CU(cudaEventRecord(h->ev_join, h->side_stream));
                 CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-            } else if ((rc = launch_pass_b(h, ob, oe, diag)) != 0) return rc;
+            } else {
+                if ((rc = unpack2(h)) != 0) return rc;
+                if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_all)) != 0) return rc;
+            }
             std::swap(h->cur.P, h->alt.P);
             if (h->gt) {
                 h->gt->end_group(KG_PASS_B);
@@ -554,20 +603,18 @@ extern "C" int sphsm_step_group(sphsm_handle **hs, int nranks, int nsteps) {
                 }
                 for (int r = 0; r < nranks; r++) CU(cudaMemcpy(hs[r]->totals, sum.data(), c * sizeof(double), cudaMemcpyHostToDevice));
             } else if (coll[0] == COLL_EXCH2) {
-                for (int r = 0; r + 1 < nranks; r++) {  // face between rank r (left) and rank r + 1 (right)
-                    sphsm_handle *a = hs[r], *b = hs[r + 1];
-                    const int na = a->dp.own_end - a->b3, nb_halo = b->dp.own_begin;       // a's last owned plane -> b's left halo
-                    const int nb = b->b2 - b->dp.own_begin, na_halo = a->n - a->dp.own_end;  // b's first owned plane -> a's right halo
-                    if (na != nb_halo || nb != na_halo) return fail(a, SPHSM_ERR_COMM, "boundary plane populations differ across a slab face");
-                    CU(cudaMemcpy(b->cur.V, a->cur.V + a->b3, (size_t)na * sizeof(float4), cudaMemcpyDeviceToDevice));
-                    CU(cudaMemcpy(b->cur.S, a->cur.S + a->b3, (size_t)na * sizeof(float2), cudaMemcpyDeviceToDevice));
-                    CU(cudaMemcpy(b->cur.VN, a->cur.VN + a->b3, (size_t)na * sizeof(float), cudaMemcpyDeviceToDevice));
-                    CU(cudaMemcpy(a->cur.V + a->dp.own_end, b->cur.V + b->dp.own_begin, (size_t)nb * sizeof(float4), cudaMemcpyDeviceToDevice));
-                    CU(cudaMemcpy(a->cur.S + a->dp.own_end, b->cur.S + b->dp.own_begin, (size_t)nb * sizeof(float2), cudaMemcpyDeviceToDevice));
-                    CU(cudaMemcpy(a->cur.VN + a->dp.own_end, b->cur.VN + b->dp.own_begin, (size_t)nb * sizeof(float), cudaMemcpyDeviceToDevice));
+                const size_t bytes = msg2_bytes(h->send_cap);
+                for (int r = 0; r < nranks; r++) {
+                    if (r > 0) CU(cudaMemcpy(hs[r]->msg_recv[0], hs[r - 1]->msg_send[1], bytes, cudaMemcpyDeviceToDevice));
+                    if (r < nranks - 1) CU(cudaMemcpy(hs[r]->msg_recv[1], hs[r + 1]->msg_send[0], bytes, cudaMemcpyDeviceToDevice));
                 }
             }
         }
+    }
+    for (int r = 0; r < nranks; r++) {  // the last step's boundaries and error counters, now
+        int rc = slab_refresh(hs[r]);
+        if (!rc) rc = slab_check_local_error(hs[r]);
+        if (rc) return rc;
     }
     return SPHSM_OK;
 }

@@ -54,16 +54,17 @@ static bool use_counting_sort(const sphsm_handle *h) {
 }
 
 // one pass over the full key: count per cell -> scan (= the cell table) -> scatter -> canonical in-cell order
-static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt) {
-    const int n = h->n, m = h->dp.num_cells + 1;  // cells + the limbo bucket
+// n_dev != nullptr (slab step): the entry count is *n_dev + n_add in device memory and h->n is an upper bound for the grids
+static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt, const int *n_dev = nullptr, int n_add = 0, int n_grid = -1) {
+    const int n = n_grid >= 0 ? n_grid : h->n, m = h->dp.num_cells + 1;  // cells + the limbo bucket
     const int tiles = cdiv(m + 1, SCAN_TILE);
     if (h->counts_ready) h->counts_ready = false;  // pass B filed keys, ranks and counts of these positions while it held them
-    else LAUNCH(k_cell_count, cdiv(n, 256), 256, h->dp, h->cur.P, h->keys[0], h->keys[1], h->cell_count);
+    else LAUNCH(k_cell_count, cdiv(n, 256), 256, h->dp, h->cur.P, h->keys[0], h->keys[1], h->cell_count, n_dev, n_add);
     if (gt) gt->end_group(KG_HASH);
     LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
     LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles, h->big_count);
     LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start);
-    LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0], h->skeys);
+    LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0], h->skeys, n_dev, n_add);
     h->key_sorted = h->skeys;
     LAUNCH(k_cell_sort_ids, cdiv(h->dp.num_cells, 256), 256, h->cell_start, h->vals[0], h->cur.ID, h->dp.num_cells, h->big_cells, h->big_count);
     LAUNCH(k_cell_sort_big, 64, 256, h->cell_start, h->vals[0], h->vals[1], h->cur.ID, h->big_cells, h->big_count);
@@ -73,9 +74,9 @@ static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt) {
     return SPHSM_OK;
 }
 
-static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
+static int grid_sort(sphsm_handle *h, GroupTimer *gt, const int *n_dev = nullptr, int n_add = 0, int n_grid = -1) {
     const int n = h->n;
-    if (use_counting_sort(h)) return grid_sort_counting(h, gt);
+    if (use_counting_sort(h) || n_dev) return grid_sort_counting(h, gt, n_dev, n_add, n_grid);  // (the slab step always sorts by counting)
     drop_counts(h);
     h->bounds_ready = false;
     const int passes = h->sort_passes;
@@ -106,8 +107,8 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt) {
 
 // fuse_goal: 0 = plain gather; 1 / 2 = gather + goal / predicted / corrected velocity (2 also stores GOAL and PV)
 // n_dev != nullptr: the live count is read from device memory (grid sized for h->n, an upper bound)
-static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool bounds_done = false, const int *n_dev = nullptr) {
-    const int n = h->n, src = h->sorted_buf;
+static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool bounds_done = false, const int *n_dev = nullptr, int n_grid = -1) {
+    const int n = n_grid >= 0 ? n_grid : h->n, src = h->sorted_buf;
     if (!bounds_done && !h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
     if (fuse_goal) {
         if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev);
@@ -177,32 +178,29 @@ static int moments_part(sphsm_handle *h) {
     // particles the full 8 x SMs grid spent most of its 32 us in the reductions)
     // Slab mode: every particle is summed by the rank that integrated it last step, i.e. over that rank's owned slot range
     // as it stood BEFORE this step's exchange (migrants on their way out included, arrivals not): each particle exactly
-    // once across ranks, and the sums need neither the exchange nor the sort, so they start with the step.
+    // once across ranks, and the sums need neither the exchange nor the sort, so they start with the step.  The range is
+    // read from device memory (the SlabMeta the previous step's sort wrote).
     DevParams d = h->dp;
-    int off = 0;
+    const int *rng = nullptr;
+    int count = d.n;
     if (d.slab_on) {
-        off = h->mom_begin;
-        d.n = h->mom_end - h->mom_begin;
+        rng = h->d_meta[h->meta_cur]->rng_all;
+        count = h->own_bound;
         d.slab_on = 0;
     }
-    const int B = std::max(1, std::min(h->red_blocks, cdiv(std::max(d.n, 1), 2048)));
-    if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, d, h->cur.P + off, h->cur.O + off, h->sm, h->partial);
-    else LAUNCH(k_moments<3>, B, 256, d, h->cur.P + off, h->cur.O + off, h->sm, h->partial);
+    const int B = std::max(1, std::min(h->red_blocks, cdiv(std::max(count, 1), 2048)));
+    if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, d, h->cur.P, h->cur.O, h->sm, h->partial, rng);
+    else LAUNCH(k_moments<3>, B, 256, d, h->cur.P, h->cur.O, h->sm, h->partial, rng);
     const int nacc = h->dp.quadratic ? 33 : 15;
     LAUNCH(k_sum_partials_par, nacc, 256, h->partial, B, nacc, h->totals);
-    if (h->comm_mode == 1) LAUNCH(k_store_double, 1, 1, h->totals + nacc, h->local_error ? 1.0 : 0.0);  // see local_error
+    if (h->comm_mode == 1) LAUNCH(k_store_flag, 1, 1, h->totals + nacc, h->d_err);  // the rank's error state rides on the allreduce
     return SPHSM_OK;
 }
-// the per-step moment allreduce (NCCL mode: + the error flag, copied back to the host for the next read-back to look at)
+// the per-step moment allreduce (NCCL mode: + the summed error flag, which the sort's k_mg_meta passes on to the host read-back)
 static int moment_allreduce(sphsm_handle *h) {
     const int nacc = h->dp.quadratic ? 33 : 15;
     if (h->comm_mode != 1 || h->nranks == 1) return comm_allreduce(h, nacc);
-    int rc = comm_allreduce(h, nacc + 1);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(h->h_flag, h->totals + nacc, sizeof(double), cudaMemcpyDeviceToHost, h->launch_stream));
-    CU(cudaEventRecord(h->ev_flag, h->launch_stream));
-    h->flag_pending = true;
-    return SPHSM_OK;
+    return comm_allreduce(h, nacc + 1);
 }
 
 static int rest_moments(sphsm_handle *h) {
@@ -334,42 +332,46 @@ static int prepare6(sphsm_handle *h, K kern, unsigned bytes) {  // dynamic share
         }                                                                                                               \
     } while (0)
 
-// slots [begin, end) minus the hole [hole_b, hole_e)
-static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0) {
+// slots [begin, end) minus the hole [hole_b, hole_e).  rng != nullptr (slab step): the range is read from device memory
+// ({begin, end, hole_begin, hole_len}) and [begin, end) / the hole only size the grid: `end - begin - hole` is an upper bound of the
+// target count, and with a hole the two sides may hold up to that many targets EACH (generation 6 cuts them into blocks separately).
+static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0, const int *rng = nullptr) {
     const int count = end - begin - (hole_e - hole_b);
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
-    if (warp_path(h)) LAUNCH(k_pass_a4w, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->cell_start, count);
-    else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start, h->key_sorted);
-    else if (g_t6 == 64) LAUNCH6(k_pass_a6<64>, 64, false, grid6(begin, end, hole_b, hole_e, 64), d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6);
-    else LAUNCH6(k_pass_a6<128>, 128, false, grid6(begin, end, hole_b, hole_e, 128), d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6);
+    const int g6_128 = rng ? cdiv(count, 128) + 2 : grid6(begin, end, hole_b, hole_e, 128), g6_64 = rng ? cdiv(count, 64) + 2 : grid6(begin, end, hole_b, hole_e, 64);
+    if (warp_path(h)) LAUNCH(k_pass_a4w, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->cell_start, count, rng);
+    else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, rng);
+    else if (g_t6 == 64) LAUNCH6(k_pass_a6<64>, 64, false, g6_64, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6, rng);
+    else LAUNCH6(k_pass_a6<128>, 128, false, g6_128, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6, rng);
     return SPHSM_OK;
 }
 template <int T, int STEP>
-static int launch_pass_b6(sphsm_handle *h, const DevParams &d, int grid, bool diag, uint32_t *nk, uint32_t *nr, uint32_t *ncnt) {
-    if (diag) LAUNCH6((k_pass_b6<T, STEP, true>), T, true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, g_stage6);
-    else LAUNCH6((k_pass_b6<T, STEP, false>), T, true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, g_stage6);
+static int launch_pass_b6(sphsm_handle *h, const DevParams &d, int grid, bool diag, uint32_t *nk, uint32_t *nr, uint32_t *ncnt, const int *rng) {
+    if (diag) LAUNCH6((k_pass_b6<T, STEP, true>), T, true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, g_stage6, rng);
+    else LAUNCH6((k_pass_b6<T, STEP, false>), T, true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, g_stage6, rng);
     return SPHSM_OK;
 }
-static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hole_b = 0, int hole_e = 0, bool file_counts = false) {
+static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hole_b = 0, int hole_e = 0, bool file_counts = false,
+                         const int *rng = nullptr) {
     uint32_t *nk = file_counts ? h->keys[0] : nullptr, *nr = file_counts ? h->keys[1] : nullptr, *ncnt = file_counts ? h->cell_count : nullptr;
     const int count = end - begin - (hole_e - hole_b);
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
     if (warp_path(h)) {
-        if (diag) LAUNCH(k_pass_b4w<true>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count);
-        else LAUNCH(k_pass_b4w<false>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count);
+        if (diag) LAUNCH(k_pass_b4w<true>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count, rng);
+        else LAUNCH(k_pass_b4w<false>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count, rng);
     } else if (g_pass_gen == 4) {
-        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt);
-        else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt);
+        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, rng);
+        else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, rng);
     } else if (g_t6 == 64) {
-        const int grid = grid6(begin, end, hole_b, hole_e, 64);
-        return g_b_step6 == 4 ? launch_pass_b6<64, 4>(h, d, grid, diag, nk, nr, ncnt) : launch_pass_b6<64, 2>(h, d, grid, diag, nk, nr, ncnt);
+        const int grid = rng ? cdiv(count, 64) + 2 : grid6(begin, end, hole_b, hole_e, 64);
+        return g_b_step6 == 4 ? launch_pass_b6<64, 4>(h, d, grid, diag, nk, nr, ncnt, rng) : launch_pass_b6<64, 2>(h, d, grid, diag, nk, nr, ncnt, rng);
     } else {
-        const int grid = grid6(begin, end, hole_b, hole_e, 128);
-        return g_b_step6 == 4 ? launch_pass_b6<128, 4>(h, d, grid, diag, nk, nr, ncnt) : launch_pass_b6<128, 2>(h, d, grid, diag, nk, nr, ncnt);
+        const int grid = rng ? cdiv(count, 128) + 2 : grid6(begin, end, hole_b, hole_e, 128);
+        return g_b_step6 == 4 ? launch_pass_b6<128, 4>(h, d, grid, diag, nk, nr, ncnt, rng) : launch_pass_b6<128, 2>(h, d, grid, diag, nk, nr, ncnt, rng);
     }
     return SPHSM_OK;
 }

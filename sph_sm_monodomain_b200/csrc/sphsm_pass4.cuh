@@ -44,11 +44,25 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 // case), so that case is answered directly: +-0 / b = +-0 for b > 0.
 __device__ __forceinline__ float div_rn_z(float a, float b) { return (a == 0.0f && b > 0.0f) ? a : __fdiv_rn(a, b); }
 
-// the k-th target slot of a launch over [own_begin, own_end) minus the hole
-__device__ __forceinline__ int launch_slot(const DevParams &p, int k) {
-    int i = p.own_begin + k;
-    if (i >= p.hole_begin) i += p.hole_len;
-    return i;
+// A launch covers the slots [begin, end) minus the hole [hole_begin, hole_begin + hole_len).  On one GPU the range is in the
+// parameter block; in the slab step it is read from device memory (rng = {begin, end, hole_begin, hole_len}, written by the
+// sort of the same step), the grid is sized for an upper bound and the surplus threads leave.
+struct Range4 {
+    int begin, end, hole_begin, hole_len;
+};
+__device__ __forceinline__ Range4 launch_range(const DevParams &p, const int *__restrict__ rng) {
+    Range4 r = {p.own_begin, p.own_end, p.hole_begin, p.hole_len};
+    if (rng) {
+        const int4 v = *reinterpret_cast<const int4 *>(rng);
+        r.begin = v.x; r.end = v.y; r.hole_begin = v.z; r.hole_len = v.w;
+    }
+    return r;
+}
+// the k-th target slot of the launch, or -1 past its end
+__device__ __forceinline__ int launch_slot(const Range4 &r, int k) {
+    int i = r.begin + k;
+    if (i >= r.hole_begin) i += r.hole_len;
+    return i < r.end ? i : -1;
 }
 
 // The in-range list lives at 32-bit shared-memory addresses held in a register (`lofs`, bytes): ptxas re-materialises the
@@ -152,11 +166,10 @@ __device__ __forceinline__ void pass_a_finish(const DevParams &p, const Arrays &
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
 __global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
-                                                const int *__restrict__ cell_start, const uint32_t *__restrict__ skey) {
+                                                const int *__restrict__ cell_start, const uint32_t *__restrict__ skey, const int *__restrict__ rng) {
     __shared__ int s_list[LIST_K * PT4];
-    int i = p.own_begin + blockIdx.x * PT4 + threadIdx.x;
-    if (i >= p.hole_begin) i += p.hole_len;
-    if (i >= p.own_end) return;
+    const int i = launch_slot(launch_range(p, rng), blockIdx.x * PT4 + threadIdx.x);
+    if (i < 0) return;
     const float4 pi = a.P[i];
     const float4 ci = a.C[i];
     const int z0 = g->zero;  // == 0, loaded from global: what is derived from it stays in registers (see list_put)
@@ -302,11 +315,11 @@ __device__ __forceinline__ void pass_b_finish(const DevParams &p, const Arrays &
 template <bool DIAG>
 __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 float4 *__restrict__ Pout, const int *__restrict__ cell_start, const uint32_t *__restrict__ skey,
-                                                uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count) {
+                                                uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count,
+                                                const int *__restrict__ rng) {
     __shared__ int s_list[LIST_K * PT4];
-    int i = p.own_begin + blockIdx.x * PT4 + threadIdx.x;
-    if (i >= p.hole_begin) i += p.hole_len;
-    if (i >= p.own_end) return;
+    const int i = launch_slot(launch_range(p, rng), blockIdx.x * PT4 + threadIdx.x);
+    if (i < 0) return;
     const float4 pi = a.P[i];
     const float4 vi = a.V[i];
     float4 e4 = a.E[i];

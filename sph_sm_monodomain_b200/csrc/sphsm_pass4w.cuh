@@ -40,10 +40,12 @@ __device__ __forceinline__ void for_each_row(const DevParams &p, const int *__re
 
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
-__global__ void __launch_bounds__(PTW) k_pass_a4w(const __grid_constant__ DevParams p, Arrays a, const int *__restrict__ cell_start, int count) {
+__global__ void __launch_bounds__(PTW) k_pass_a4w(const __grid_constant__ DevParams p, Arrays a, const int *__restrict__ cell_start, int count,
+                                                  const int *__restrict__ rng) {
     const int w = (blockIdx.x * PTW + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= count) return;
-    const int i = launch_slot(p, w);
+    const int i = launch_slot(launch_range(p, rng), w);
+    if (i < 0) return;
     const float4 pi = a.P[i];
     const float4 ci = a.C[i];
     const float4 *__restrict__ P = a.P;
@@ -84,10 +86,12 @@ __global__ void __launch_bounds__(PTW) k_pass_a4w(const __grid_constant__ DevPar
 template <bool DIAG>
 __global__ void __launch_bounds__(PTW) k_pass_b4w(const __grid_constant__ DevParams p, Arrays a, float4 *__restrict__ Pout,
                                                   const int *__restrict__ cell_start, uint32_t *__restrict__ next_keys,
-                                                  uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count, int count) {
+                                                  uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count, int count,
+                                                  const int *__restrict__ rng) {
     const int w = (blockIdx.x * PTW + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= count) return;
-    const int i = launch_slot(p, w);
+    const int i = launch_slot(launch_range(p, rng), w);
+    if (i < 0) return;
     const float4 pi = a.P[i];
     const float4 vi = a.V[i];
     float4 e4 = a.E[i];

@@ -95,15 +95,15 @@ struct Lay6 {
 // the slot range of block `b` of a launch over [own_begin, own_end) minus the hole: blocks never straddle the hole, so a block's
 // targets are consecutive slots.  Host side: grid6() gives the matching block count.
 template <int T>
-__device__ __forceinline__ void block_range6(const DevParams &p, int b, int &base, int &end) {
-    const int len1 = p.hole_len > 0 ? p.hole_begin - p.own_begin : p.own_end - p.own_begin;
+__device__ __forceinline__ void block_range6(const Range4 &r, int b, int &base, int &end) {
+    const int len1 = r.hole_len > 0 ? r.hole_begin - r.begin : r.end - r.begin;
     const int nb1 = (len1 + T - 1) / T;
     if (b < nb1) {
-        base = p.own_begin + b * T;
-        end = p.own_begin + len1;
+        base = r.begin + b * T;
+        end = r.begin + len1;
     } else {
-        base = p.hole_begin + p.hole_len + (b - nb1) * T;
-        end = p.own_end;
+        base = r.hole_begin + r.hole_len + (b - nb1) * T;
+        end = r.end;
     }
 }
 
@@ -266,12 +266,13 @@ __device__ __forceinline__ void pass_a6_neighbours(const DevParams *__restrict__
 
 template <int T>
 __global__ void __launch_bounds__(T, 768 / T) k_pass_a6(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
-                                               const int *__restrict__ cell_start, const uint32_t *__restrict__ skey, int stage_on) {
+                                               const int *__restrict__ cell_start, const uint32_t *__restrict__ skey, int stage_on,
+                                               const int *__restrict__ rng) {
     using L = Lay6<T, false>;
     extern __shared__ __align__(128) uint8_t smem6[];
     const unsigned smem0 = smem_u32(smem6);
     int base, end;
-    block_range6<T>(p, blockIdx.x, base, end);
+    block_range6<T>(launch_range(p, rng), blockIdx.x, base, end);
     const int i = base + threadIdx.x;
     const bool live = i < end;
     const int key = live ? (int)skey[i] : p.num_cells;
@@ -409,12 +410,12 @@ template <int T, int STEP, bool DIAG>
 __global__ void __launch_bounds__(T, 640 / T) k_pass_b6(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                float4 *__restrict__ Pout, const int *__restrict__ cell_start, const uint32_t *__restrict__ skey,
                                                uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count,
-                                               int stage_on) {
+                                               int stage_on, const int *__restrict__ rng) {
     using L = Lay6<T, true>;
     extern __shared__ __align__(128) uint8_t smem6[];
     const unsigned smem0 = smem_u32(smem6);
     int base, end;
-    block_range6<T>(p, blockIdx.x, base, end);
+    block_range6<T>(launch_range(p, rng), blockIdx.x, base, end);
     const int i = base + threadIdx.x;
     const bool live = i < end;
     const int key = live ? (int)skey[i] : p.num_cells;

@@ -299,16 +299,17 @@ __global__ void k_rest_finalize2(const double *__restrict__ tot, SmState *sm, fl
 }
 
 // per-step sums: [0..2] sum m' x, [3..5] sum m x, [6 + a*NB + b] sum m x_a q9_b   (NB = 3 linear, 9 quadratic)
+// rng != nullptr: the slots [rng[0], rng[1]) are summed, read from device memory (slab step: the rank's owned range)
 template <int NB>
 __global__ void __launch_bounds__(256) k_moments(const __grid_constant__ DevParams p, const float4 *__restrict__ P, const float4 *__restrict__ O,
-                                                 const SmState *sm, double *partial) {
-    const int n = p.n;
+                                                 const SmState *sm, double *partial, const int *__restrict__ rng) {
+    const int first = rng ? rng[0] : 0, n = rng ? rng[1] : p.n;
     constexpr int NACC = 6 + 3 * NB;
     const float ox = sm->ocm[0], oy = sm->ocm[1], oz = sm->ocm[2];
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; k++) acc[k] = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 q4 = P[i];
         if (p.slab_on && !slab_owned(p, q4)) continue;
         float4 o = O[i];

@@ -250,10 +250,12 @@ __global__ void __launch_bounds__(256) k_cell_bounds(const uint32_t *__restrict_
 // k_cell_bounds disappears), scatter, and a per-cell ordering by original index that makes the result deterministic and
 // equal to the reference's bucket order (push_back order, cpp:207-212).  The LSD radix sort above remains the path for
 // grids with far more cells than particles, where a pass over the cell table would cost more than sorting the keys.
+// n_dev != nullptr: the entry count is *n_dev + n_add, read from device memory (slab step: the grid is sized for an upper bound)
 __global__ void __launch_bounds__(256) k_cell_count(const __grid_constant__ DevParams p, const float4 *__restrict__ P, uint32_t *__restrict__ keys,
-                                                    uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count) {
+                                                    uint32_t *__restrict__ rank, uint32_t *__restrict__ cell_count, const int *__restrict__ n_dev,
+                                                    int n_add) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < p.n;
+    const bool live = i < (n_dev ? *n_dev + n_add : p.n);
     uint32_t key = (uint32_t)p.num_cells;
     if (live) {
         const float4 q = P[i];
@@ -396,9 +398,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restric
 // skey[slot] = the key again, in slot order (the in-cell ordering below permutes slots of ONE cell, so it stays valid): the
 // neighbour passes read it instead of recomputing cell coordinates
 __global__ void __launch_bounds__(256) k_cell_scatter(int n, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
-                                                      const int *__restrict__ cell_start, uint32_t *__restrict__ vals, uint32_t *__restrict__ skey) {
+                                                      const int *__restrict__ cell_start, uint32_t *__restrict__ vals, uint32_t *__restrict__ skey,
+                                                      const int *__restrict__ n_dev, int n_add) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= (n_dev ? *n_dev + n_add : n)) return;
     const uint32_t key = keys[i], slot = (uint32_t)cell_start[key] + rank[i];
     vals[slot] = (uint32_t)i;
     skey[slot] = key;

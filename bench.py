@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — particle-steps/s of the full SPH + shape-matching + monodomain step (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 8m|1m|32m|<nx>x<ny>x<nz>]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 8m|8m_jitter|1m|32m|cfg1|cfg2|<nx>x<ny>x<nz>]
 
 A "step" is one Animation() of the whole particle set: neighbour search (hash, counting sort = cell table, reorder),
 shape matching (moments, polar decomposition, goal positions), both neighbour passes, ionic model, integration.
@@ -12,12 +12,15 @@ rule) and far larger than L2 (8M x 68 B of persistent state = 544 MB vs 126 MB),
 timed steps.
 
 One JSON line on stdout (rank 0).  `value` = device-resident throughput (CUDA events around exactly K steps, max over
-ranks); `e2e` = the same metric through the C-ABI with HOST buffers: every step uploads the per-particle stimulation
-array from pinned host memory (the per-step control input of this path) and downloads the positions (what the
-reference's viewer reads through Get_Paticles() every frame), using the library's asynchronous I/O calls so that the
-copies of step k overlap the compute of step k+1; the timed region ends when the last result is in host memory.  `roofline` is the dominant kernel (fused pass B) from
+ranks); `e2e` = the same metric through the C-ABI with HOST buffers: every step uploads the stimulation values of the
+particles the rank owns from pinned host memory (the per-step control input of this path; 4 B per particle in total,
+whatever the number of ranks) and downloads their positions (what the reference's viewer reads through Get_Paticles()
+every frame), using the library's asynchronous I/O calls so that the copies of step k overlap the compute of step k+1;
+the timed region ends when the last result is in host memory.  `roofline` is the dominant kernel (fused pass B) from
 CUDA events on the handle's stream; `cpu_baseline` is the reference's own CPU step timed on this box (1 thread — the
-reference has no threading) on a bounded sample.
+reference has no threading) on a bounded sample.  With N > 1 the line also carries `mg_parity`: a small lattice stepped
+through the same slab path on all ranks and compared with a single-GPU run on rank 0 before the timed region.  With
+N = 1 and the default workload it carries `also`: quick measurements of the other configurations in the same process.
 """
 from __future__ import annotations
 
@@ -48,7 +51,10 @@ PASS_B_NAME = "pass_b(cell+force+laplacian+integrate)"
 WORKLOADS = {
     "1m": dict(dims=(100, 100, 100), quadratic=False, name="synthetic 1M-particle cubic lattice, linear shape matching (configs[2])"),
     "8m": dict(dims=(512, 125, 125), quadratic=True, name="synthetic 8M-particle elongated lattice 512x125x125, quadratic shape matching (configs[3])"),
-    "32m": dict(dims=(800, 200, 200), quadratic=False, name="synthetic 32M-particle lattice 800x200x200, monodomain pacing (configs[4])"),
+    "32m": dict(dims=(800, 200, 200), quadratic=False, pacing=(50, 25),
+                name="synthetic 32M-particle lattice 800x200x200, monodomain pacing: stimulus on the end slab every 50 steps, turnOffStim 25 steps later (configs[4])"),
+    "8m_jitter": dict(dims=(512, 125, 125), quadratic=True, jitter=0.05,
+                      name="synthetic 8M-particle lattice 512x125x125 with seeded jitter U(-0.05 s, 0.05 s) per coordinate (SURVEY 8d.3), quadratic shape matching"),
 }
 # BASELINE.json configs[0] / configs[1]: the reference's own particle sets (Resources/*.csv through main.cpp's loader rule,
 # turnOnStim_Mesh), taken from the committed golden fixtures (tests/golden/, generated from the genuine reference by
@@ -56,8 +62,9 @@ WORKLOADS = {
 # CPU-vs-GPU comparison on the reference's own inputs, not as the headline.
 WORKLOADS["cfg1"] = dict(golden="cfg1_4944", quadratic=False, name="Resources/biceps_simple_out_4944.csv, main.cpp defaults (configs[0])")
 WORKLOADS["cfg2"] = dict(golden="cfg2_5211", quadratic=False, name="Resources/biceps_simple_out_18475.csv subsampled to 5211 (configs[1])")
-CPU_SAMPLE_DIMS = (40, 40, 40)  # bounded sample for the CPU legs: 64k particles of the same lattice / SM mode
-CPU_SAMPLE_STEPS = 200          # ~10-15 s of single-thread CPU work at ~1.2e6 particle-steps/s
+CPU_SAMPLE_DIMS = (100, 100, 100)  # bounded sample for the CPU legs: a 1M-particle lattice of the same spacing / SM mode (~0.9 s per step)
+CPU_SAMPLE_STEPS = 10              # ~10 s of single-thread CPU work at ~1.2e6 particle-steps/s
+FIXED_WARMUP = 400                 # untimed steps before the timed region, the same for every N (>= 0.1 s under load at N = 8, 0.6 s at N = 1)
 
 
 def parse_workload(s):
@@ -73,13 +80,13 @@ def workload_inputs(wl):
         g = np.load(os.path.join(ROOT, "tests", "golden", wl["golden"] + ".npz"))
         return (np.ascontiguousarray(g["positions"], dtype=np.float32), (1.5, 1.5, 1.5), g["init.fixed"].astype(np.uint8),
                 g["init.stim"].astype(np.float32))
-    return make_lattice(wl["dims"])
+    return make_lattice(wl["dims"], wl.get("jitter", 0.0))
 
 
-def make_lattice(dims):
+def make_lattice(dims, jitter=0.0):
     from sph_sm_monodomain_b200 import inputs
 
-    pos, world = inputs.lattice(*dims)
+    pos, world = inputs.lattice(*dims, jitter=jitter)
     fixed, stim = inputs.lattice_masks(pos, dims[0], 8)
     return pos, world, fixed.astype(np.uint8), np.where(stim, np.float32(300.0), np.float32(0.0)).astype(np.float32)
 
@@ -153,7 +160,7 @@ def cpu_reference_rate(quadratic, steps, warmup, backend=None, wl=None):
     if backend is None:
         backend = "ref_ofast" if "ref_ofast" in avail else ("ref" if "ref" in avail else "port")
     whole = wl is not None and "golden" in wl  # the reference's own sets are small enough to run as they are
-    pos, world, fixed, stim = workload_inputs(wl) if whole else make_lattice(CPU_SAMPLE_DIMS)
+    pos, world, fixed, stim = workload_inputs(wl) if whole else make_lattice(CPU_SAMPLE_DIMS, (wl or {}).get("jitter", 0.0))
     sim = CpuSim(backend, capacity=len(pos), world=world)
     sim.Init_Fluid(pos)
     sim.set_fields(fixed=fixed, stim=stim)
@@ -175,10 +182,12 @@ def cpu_reference_rate(quadratic, steps, warmup, backend=None, wl=None):
 def run_reference(args, wl, rank, world_size):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 100))  # each "step" of this arm is one CPU step of the bounded sample (~50 ms)
-    base = cpu_reference_rate(wl["quadratic"], steps, min(args.warmup, 3), wl=wl)
+    whole = "golden" in wl
+    steps = max(1, min(args.steps, 100 if whole else 20))  # each "step" of this arm is one CPU step of the bounded sample (~0.9 s at 1M)
+    warmup = min(args.warmup, 100 if whole else 5)
+    base = cpu_reference_rate(wl["quadratic"], steps, warmup, wl=wl)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 3), "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "warmup": warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": base["sample"]},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -188,10 +197,137 @@ def run_reference(args, wl, rank, world_size):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def stim_box_of(pos, dims):
+    """The end slab the masks stimulate (inputs.lattice_masks: the first 8 x-layers) as an axis-aligned box."""
+    from sph_sm_monodomain_b200 import inputs
+
+    s = float(inputs.KERNEL_H) * 0.9
+    x0 = float(pos[:, 0].min())
+    return (-1.0, -1.0, -1.0), (x0 + 8 * s - 0.5 * s, 1e9, 1e9)
+
+
+def make_sim(pos, world, fixed, stim, quadratic, device, world_size, rank, dist, torch, parts=None, axis=None, **kw):
+    """A handle with the workload loaded; with world_size > 1 also its NCCL communicator (id broadcast from rank 0) and slab."""
+    from sph_sm_monodomain_b200 import Sim
+
+    n_total = len(pos)
+    if world_size > 1:
+        sim = Sim(capacity=n_total, world=world, device=device, diagnostics=False, slab_axis=axis, **kw)
+    else:
+        sim = Sim(capacity=n_total, world=world, device=device, diagnostics=False, **kw)
+    sim.Init_Fluid(pos)
+    sim.set_masks(fixed, stim)
+    if quadratic:
+        sim.flip_quadratic()
+    if world_size > 1:
+        ident = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(Sim.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, 0)
+        sim.comm_init(world_size, rank, bytes(ident.cpu().numpy().tobytes()))
+        sim.set_slab(*parts[rank])
+    return sim
+
+
+def mg_parity_check(device, world_size, rank, dist, torch):
+    """Multi-GPU correctness inside the bench run: a ~55k-particle jittered lattice stepped 10 times through the slab path on
+    all ranks (its own NCCL communicator, the same library code the timed region runs) and on rank 0's GPU alone; with the
+    canonical in-cell order both runs sum in the same order, so the positions must agree bit for bit."""
+    from sph_sm_monodomain_b200 import Sim, inputs, slabs
+
+    dims, steps = (96, 24, 24), 10
+    pos, world = inputs.lattice(*dims, jitter=0.05)
+    fixed, stim = inputs.lattice_masks(pos, dims[0], 4)
+    fixed, stim = fixed.astype(np.uint8), np.where(stim, np.float32(300), np.float32(0)).astype(np.float32)
+    n = len(pos)
+    axis = slabs.slab_axis_for(world)
+    parts = slabs.partition_planes(slabs.plane_histogram(pos, axis, slabs.num_planes(world, axis)), world_size)
+
+    def canonical(s):
+        p = s.get_params()
+        p.reserved[1] = 1
+        s._ck(s.lib.sphsm_set_params(s.h, p))
+
+    sim = Sim(capacity=n, world=world, device=device, diagnostics=False, slab_axis=axis)
+    sim.Init_Fluid(pos)
+    sim.set_masks(fixed, stim)
+    canonical(sim)
+    ident = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
+    if rank == 0:
+        ident.copy_(torch.frombuffer(bytearray(Sim.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(ident, 0)
+    sim.comm_init(world_size, rank, bytes(ident.cpu().numpy().tobytes()))
+    sim.set_slab(*parts[rank])
+    sim.Animation(steps)
+    sim.sync()
+    ids, xyz = sim.download_owned()
+    cnt = torch.tensor([len(ids)], device=f"cuda:{device}")
+    cnts = [torch.zeros_like(cnt) for _ in range(world_size)]
+    dist.all_gather(cnts, cnt)
+    cap = int(max(c.item() for c in cnts))
+    pad_ids = torch.full((cap,), -1, dtype=torch.int32, device=f"cuda:{device}")
+    pad_xyz = torch.zeros((cap, 3), dtype=torch.float32, device=f"cuda:{device}")
+    pad_ids[: len(ids)] = torch.from_numpy(ids).to(pad_ids.device)
+    pad_xyz[: len(ids)] = torch.from_numpy(xyz).to(pad_xyz.device)
+    all_ids = [torch.zeros_like(pad_ids) for _ in range(world_size)]
+    all_xyz = [torch.zeros_like(pad_xyz) for _ in range(world_size)]
+    dist.all_gather(all_ids, pad_ids)
+    dist.all_gather(all_xyz, pad_xyz)
+    sim.close()
+    res = None
+    if rank == 0:
+        got = np.full((n, 3), np.nan, np.float32)
+        seen = np.zeros(n, np.int32)
+        for i, x in zip(all_ids, all_xyz):
+            i, x = i.cpu().numpy(), x.cpu().numpy()
+            m = i >= 0
+            got[i[m]] = x[m]
+            seen[i[m]] += 1
+        single = Sim(capacity=n, world=world, device=device, diagnostics=False, slab_axis=axis)
+        single.Init_Fluid(pos)
+        single.set_masks(fixed, stim)
+        canonical(single)
+        single.Animation(steps)
+        i1, x1 = single.download_owned()
+        single.close()
+        ref = np.empty((n, 3), np.float32)
+        ref[i1] = x1
+        once = bool((seen == 1).all())
+        res = {"particles": n, "steps": steps, "ranks": world_size, "every_particle_owned_once": once,
+               "bit_identical": bool(once and np.array_equal(got, ref)),
+               "max_rel": float(np.abs(got.astype(np.float64) - ref).max() / np.abs(ref).max()) if once else None,
+               "owned_per_rank": [int(c.item()) for c in cnts]}
+    dist.barrier()
+    return res
+
+
+def quick_measure(key, device, steps=30, warmup=60):
+    """Device-resident ms/step of another configuration in this process (the `also` block of the default N = 1 line)."""
+    from sph_sm_monodomain_b200 import Sim
+
+    wl = parse_workload(key)
+    pos, world, fixed, stim = workload_inputs(wl)
+    sim = Sim(capacity=len(pos), world=world, device=device, diagnostics=False)
+    sim.Init_Fluid(pos)
+    sim.set_masks(fixed, stim)
+    if wl["quadratic"]:
+        sim.flip_quadratic()
+    sim.Animation(warmup)
+    sim.sync()
+    sim.Animation(steps)
+    sim.sync()
+    ms = sim.last_step_ms() / steps
+    groups = sim.profile_step(5)
+    sim.close()
+    return {"workload": wl["name"], "particles": len(pos), "steps": steps, "warmup": warmup, "ms_per_step": ms,
+            "value": len(pos) / (ms * 1e-3), "unit": UNIT,
+            "kernel_group_ms": {k: v for k, v in groups.items() if v > 0}}
+
+
 def run_ours(args, wl, rank, world_size, local_rank):
     import torch
 
-    from sph_sm_monodomain_b200 import Sim, _capi
+    from sph_sm_monodomain_b200 import _capi
     import ctypes as C
 
     if not torch.cuda.is_available():
@@ -203,8 +339,10 @@ def run_ours(args, wl, rank, world_size, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
+    mg_parity = mg_parity_check(device, world_size, rank, dist, torch) if world_size > 1 else None
     pos, world, fixed, stim = workload_inputs(wl)
     n_total = len(pos)
+    parts = axis = None
     if world_size > 1:
         # slab decomposition along the longest axis: every rank uploads the global set, then keeps the
         # cell planes the balanced partition gives it; halos / migrants travel by ncclSend/ncclRecv inside sphsm_step
@@ -213,24 +351,14 @@ def run_ours(args, wl, rank, world_size, local_rank):
         axis = slabs.slab_axis_for(world)
         npl = slabs.num_planes(world, axis)
         parts = slabs.partition_planes(slabs.plane_histogram(pos, axis, npl), world_size)
-        sim = Sim(capacity=n_total, world=world, device=device, diagnostics=False, slab_axis=axis)
-    else:
-        sim = Sim(capacity=n_total, world=world, device=device, diagnostics=False)
-    sim.Init_Fluid(pos)
-    sim.set_masks(fixed, stim)
-    if wl["quadratic"]:
-        sim.flip_quadratic()
+    sim = make_sim(pos, world, fixed, stim, wl["quadratic"], device, world_size, rank, dist, torch, parts, axis)
     if world_size > 1:
-        ident = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{device}")
-        if rank == 0:
-            ident.copy_(torch.frombuffer(bytearray(Sim.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(ident, 0)
-        sim.comm_init(world_size, rank, bytes(ident.cpu().numpy().tobytes()))
-        sim.set_slab(*parts[rank])
         info = sim.comm_info()
         n_local = info["own_end"] - info["own_begin"]
     else:
         n_local = sim.n
+    pacing = wl.get("pacing")
+    box_lo, box_hi = stim_box_of(pos, wl["dims"]) if pacing else (None, None)
 
     def barrier():
         if dist is not None:
@@ -238,21 +366,42 @@ def run_ours(args, wl, rank, world_size, local_rank):
         sim.sync()
         torch.cuda.synchronize()
 
+    def advance(nsteps, start):
+        """nsteps steps from step number `start`; a pacing workload (configs[4]) stimulates the end slab every `period` steps
+        and calls turnOffStim `off_after` steps later (reference cpp:704-717, 764-783) inside the timed region."""
+        if not pacing:
+            sim.Animation(nsteps)
+            return
+        period, off_after = pacing
+        k, end = start, start + nsteps
+        while k < end:
+            ph = k % period
+            if ph == 0:
+                sim.set_stim_box(box_lo, box_hi, 300.0)
+            if ph == off_after:
+                sim.turnOffStim()
+            nxt = min(end, k - ph + (off_after if ph < off_after else period))
+            sim.Animation(nxt - k)
+            k = nxt
+
     # ---- device-resident throughput -----------------------------------------------------------------------------
     # clocks / throttle reasons are sampled from before the warm-up until after the timed region (a strong-scaled timed
-    # region can be shorter than one nvidia-smi sampling period, so the warm-up steps keep the GPU under the same load)
+    # region can be shorter than one nvidia-smi sampling period, so the warm-up steps keep the GPU under the same load);
+    # the warm-up is the same number of steps for every N
     sampler = ClockSampler(device)
     sampler.start()
-    prewarm = max(args.warmup, int(0.35 / max(5e-5, 2.5e-10 * n_total / world_size)))  # >= ~0.35 s under load for the sampler
-    sim.Animation(prewarm)
+    prewarm = max(args.warmup, FIXED_WARMUP)
+    advance(prewarm, 0)
     barrier()
     sim.reset_launch_count()
     barrier()
     t0 = time.perf_counter()
-    sim.Animation(args.steps)
+    sim.timer_mark(0)
+    advance(args.steps, prewarm)
+    sim.timer_mark(1)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    ev_ms = sim.last_step_ms()
+    ev_ms = sim.timer_ms()
     clocks = sampler.stop()
     launches = sim.launch_count()
     t = torch.tensor([ev_ms, wall_ms], dtype=torch.float64, device=f"cuda:{device}")
@@ -269,48 +418,66 @@ def run_ours(args, wl, rank, world_size, local_rank):
     if world_size > 1:
         info = sim.comm_info()
         n_local = info["own_end"] - info["own_begin"]
-    pb_bytes = PASS_B_BYTES_PER_PARTICLE + (PASS_B_FUSED_HASH_BYTES if world_size == 1 else 0)
-    achieved = pb_bytes * n_local / (pb_ms * 1e-3) / 1e9
+    achieved = PASS_B_BYTES_PER_PARTICLE * n_local / (pb_ms * 1e-3) / 1e9
     roofline = {"kernel": "k_pass_b4 (fused cell model + force + Laplacian + integration"
                           + (" + next step's cell key / rank / count)" if world_size == 1 else ")"),
                 "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_particle": pb_bytes, "ms_per_launch": pb_ms,
+                "algorithmic_bytes_per_particle": PASS_B_BYTES_PER_PARTICLE,
+                "extra_bytes_per_particle_not_counted": {"next step's sort input filed by the same kernel (key + rank)": PASS_B_FUSED_HASH_BYTES if world_size == 1 else 0},
+                "particles_per_launch": int(n_local), "ms_per_launch": pb_ms,
                 "whole_step": {"achieved": STEP_BYTES_PER_PARTICLE * n_total / (ev_ms / args.steps * 1e-3) / 1e9,
-                               "algorithmic_bytes_per_particle": STEP_BYTES_PER_PARTICLE},
+                               "algorithmic_bytes_per_particle": STEP_BYTES_PER_PARTICLE, "peak": peak * world_size,
+                               "peak_note": f"{world_size} x the single-GPU measured peak"},
                 "kernel_group_ms": groups}
-    roofline["whole_step"]["frac"] = roofline["whole_step"]["achieved"] / peak
+    roofline["whole_step"]["frac"] = roofline["whole_step"]["achieved"] / (peak * world_size)
     traffic_file = os.path.join(ROOT, "profiles", "pass_b_traffic.json")
-    if os.path.exists(traffic_file):
+    if world_size == 1 and os.path.exists(traffic_file):  # (an ncu capture of one launch at N = 1; no per-N capture exists)
         with open(traffic_file) as fh:
             tr = json.load(fh)
         if tr.get("workload") == wl["key"]:
             roofline["traffic"] = tr.get("dram_bytes_per_launch")
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------------------
-    stim_host = torch.from_numpy(stim.copy()).pin_memory()
     own_cap = n_total if world_size == 1 else min(n_total, int(n_local * 1.25) + 65536)  # owned counts drift with migration
+    stim_by_id = stim.copy()
+    stim_host = torch.zeros((own_cap,), dtype=torch.float32).pin_memory()
     pos_host = torch.empty((own_cap, 3), dtype=torch.float32).pin_memory()
     ids_host = torch.empty((own_cap,), dtype=torch.int32).pin_memory()
+    cnt_host = torch.zeros((4,), dtype=torch.int32).pin_memory()
     lib = sim.lib
     FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int)
     stim_ptr = C.cast(stim_host.data_ptr(), FP)
     pos_ptr = C.cast(pos_host.data_ptr(), FP)
     ids_ptr = C.cast(ids_host.data_ptr(), IP)
-    own_cnt = C.c_int()
+    cnt_ptr = C.cast(cnt_host.data_ptr(), IP)
     e2e_steps = max(3, min(args.steps, 20))
+    sent = {"n": 0}
+
+    stim_all = torch.from_numpy(stim.copy()).pin_memory() if world_size == 1 else None
+    stim_all_ptr = C.cast(stim_all.data_ptr(), FP) if world_size == 1 else None
 
     def e2e_step():
         # The library's asynchronous I/O calls: every step's inputs cross PCIe host -> device and every step's result
         # device -> host, on copy streams beside the compute stream (the result of step k lands while step k+1 runs).
-        # H2D: the per-particle stimulation array (4 B / particle; every rank holds the global mask, ids are global)
-        _capi.check(lib, sim.h, lib.sphsm_set_masks_async(sim.h, None, stim_ptr, n_total))
-        _capi.check(lib, sim.h, lib.sphsm_step(sim.h, 1))
-        if world_size == 1:  # D2H: positions in the caller's order, 12 B / particle
+        if world_size == 1:
+            # H2D: the per-particle stimulation array (4 B / particle); D2H: positions in the caller's order (12 B / particle)
+            _capi.check(lib, sim.h, lib.sphsm_set_masks_async(sim.h, None, stim_all_ptr, n_total))
+            _capi.check(lib, sim.h, lib.sphsm_step(sim.h, 1))
             _capi.check(lib, sim.h, lib.sphsm_download_positions_async(sim.h, pos_ptr, n_total))
-        else:                # D2H: (id, position) of the particles this rank owns, 16 B / particle
-            _capi.check(lib, sim.h, lib.sphsm_download_owned_async(sim.h, ids_ptr, pos_ptr, own_cap, C.byref(own_cnt)))
+            return
+        # H2D: the stimulation value of every particle the rank owns, in the order of its last download (4 B / particle)
+        _capi.check(lib, sim.h, lib.sphsm_set_stim_owned_async(sim.h, stim_ptr, sent["n"]))
+        _capi.check(lib, sim.h, lib.sphsm_step(sim.h, 1))
+        # D2H: (id, position) of the particles the rank owns, 16 B / particle
+        _capi.check(lib, sim.h, lib.sphsm_download_owned_async(sim.h, ids_ptr, pos_ptr, own_cap, cnt_ptr))
 
+    if world_size > 1:
+        # prime: one download tells the host which particles it owns and in which order; their stimulation values follow that order
+        _capi.check(lib, sim.h, lib.sphsm_download_owned_async(sim.h, ids_ptr, pos_ptr, own_cap, cnt_ptr))
+        _capi.check(lib, sim.h, lib.sphsm_sync(sim.h))
+        sent["n"] = min(int(cnt_host[0]), own_cap)
+        stim_host[: sent["n"]] = torch.from_numpy(stim_by_id[ids_host.numpy()[: sent["n"]]])
     for _ in range(2):
         e2e_step()
     _capi.check(lib, sim.h, lib.sphsm_sync(sim.h))
@@ -321,23 +488,34 @@ def run_ours(args, wl, rank, world_size, local_rank):
     _capi.check(lib, sim.h, lib.sphsm_sync(sim.h))  # the last step's result is in host memory
     barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{device}")
+    n_read = n_total if world_size == 1 else min(int(cnt_host[0]), own_cap)
+    te = torch.tensor([e2e_s, float(sent["n"]), float(own_cap)], dtype=torch.float64, device=f"cuda:{device}")
+    tsum = te.clone()
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    h2d = 4 * n_total * world_size
-    d2h = 12 * n_total if world_size == 1 else 16 * n_total
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    h2d = 4 * n_total if world_size == 1 else 4 * int(tsum[1])
+    d2h = 12 * n_total if world_size == 1 else 16 * int(tsum[2]) + 4 * world_size
     e2e = {"value": n_total * e2e_steps / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-           "protocol": "per step: sphsm_set_masks_async(stim) from pinned host memory -> sphsm_step(1) -> "
-                       + ("sphsm_download_positions_async" if world_size == 1
-                          else "sphsm_download_owned_async (ids + positions of the rank's slab)")
+           "protocol": ("per step: sphsm_set_masks_async(stim, 4 B per particle) from pinned host memory -> sphsm_step(1) -> "
+                        "sphsm_download_positions_async (12 B per particle)" if world_size == 1 else
+                        "per step and rank: sphsm_set_stim_owned_async (stimulation of the rank's own particles, 4 B each, pinned host memory) -> "
+                        "sphsm_step(1) -> sphsm_download_owned_async (ids + positions of the rank's particles, 16 B each, a fixed 1.25 x slab-sized "
+                        "window because the owned count is only known on the device)")
                        + " to pinned host memory; copies overlap the next step on the library's copy streams, the timed region "
                          "ends when the last result is in host memory (sphsm_sync); bytes summed over ranks"}
-    n_read = n_total if world_size == 1 else own_cnt.value
     assert np.isfinite(pos_host.numpy()[:n_read]).all()
 
+    also = None
+    if rank == 0 and world_size == 1 and wl["key"] == "8m" and not args.no_also:
+        sim.close()
+        also = {}
+        for key in ("1m", "8m_jitter", "cfg1", "cfg2"):
+            also[key] = quick_measure(key, device, steps=30 if key in ("1m", "8m_jitter") else 200, warmup=60 if key in ("1m", "8m_jitter") else 300)
+
     if rank == 0:
-        cpu = cpu_reference_rate(wl["quadratic"], CPU_SAMPLE_STEPS, 2, wl=wl) if not args.no_cpu_baseline else None
+        cpu = cpu_reference_rate(wl["quadratic"], CPU_SAMPLE_STEPS, 1, wl=wl) if not args.no_cpu_baseline else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -349,6 +527,12 @@ def run_ours(args, wl, rank, world_size, local_rank):
                            "warmup_steps_run": prewarm},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "wall_ms_per_step": wall_ms / args.steps,
                 "roofline": roofline}
+        if pacing:
+            line["config"]["pacing"] = {"stimulate_every": pacing[0], "turn_off_after": pacing[1], "inside_timed_region": True}
+        if mg_parity is not None:
+            line["mg_parity"] = mg_parity
+        if also is not None:
+            line["also"] = also
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores_available")}
         print(json.dumps(line), flush=True)
@@ -364,6 +548,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="8m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the quick measurements of the other configurations (N = 1, default workload)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -140,6 +140,9 @@ int sphsm_stim_mesh(sphsm_handle *h, const float *xyz, int n);
 int sphsm_stim_cube(sphsm_handle *h, const float *xyz, int n);
 /* turnOffStim, cpp:764-783 */
 int sphsm_stim_off(sphsm_handle *h);
+/* set_stim (cpp:704-717) for every particle inside the axis-aligned box [lo, hi]: what turnOnStim_Cube's loop of set_stim calls
+ * over a block of positions amounts to, as one O(N) kernel (pacing protocols stimulate an end slab every few steps). */
+int sphsm_set_stim_box(sphsm_handle *h, const float lo[3], const float hi[3], float strength);
 /* Overwrite the per-particle fixed flags / stimulation values (original particle order, n entries each; either
  * pointer may be NULL).  The reference's callers do this by writing through Get_Paticles(). */
 int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const float *stim, int n);
@@ -157,7 +160,12 @@ int sphsm_sync(sphsm_handle *h);
  * directions while the compute stream keeps stepping; each call orders itself after the previous call of its kind. */
 int sphsm_set_masks_async(sphsm_handle *h, const uint8_t *fixed, const float *stim, int n);
 int sphsm_download_positions_async(sphsm_handle *h, float *xyz, int n);
+/* (multi-GPU: the owned range is only known on the device, so up to `cap` records cross and *count is written with them:
+ * like the arrays it is valid once sphsm_io_wait or sphsm_sync has returned; `count` should point into page-locked memory) */
 int sphsm_download_owned_async(sphsm_handle *h, int *ids, float *xyz, int cap, int *count);
+/* Stimulation input for the particles this rank owns: stim[k] belongs to the k-th particle of the most recent
+ * sphsm_download_owned_async on this handle (4 bytes per owned particle; the multi-GPU form of the per-step mask upload). */
+int sphsm_set_stim_owned_async(sphsm_handle *h, const float *stim, int count);
 int sphsm_io_wait(sphsm_handle *h);
 
 /* Snapshot / restart (the reference has none).  The file holds the tunable parameters and every particle in the
@@ -196,6 +204,10 @@ int sphsm_get_launch_count(sphsm_handle *h, long long *launches);
 int sphsm_reset_launch_count(sphsm_handle *h);
 /* Device time (ms, CUDA events on the handle's stream) of the last sphsm_step call's nsteps steps in total. */
 int sphsm_last_step_ms(sphsm_handle *h, float *ms);
+/* A device-side stopwatch over any sequence of calls: sphsm_timer_mark(h, 0) ... sphsm_timer_mark(h, 1), then sphsm_timer_ms
+ * gives the device time of everything queued on the handle's stream between the two marks. */
+int sphsm_timer_mark(sphsm_handle *h, int which);
+int sphsm_timer_ms(sphsm_handle *h, float *ms);
 /* Average device time (ms per launch) of each kernel group inside the last profiled step, see bench.py. */
 #define SPHSM_NUM_KERNEL_GROUPS 8
 int sphsm_profile_step(sphsm_handle *h, int nsteps, float out_ms[SPHSM_NUM_KERNEL_GROUPS]);

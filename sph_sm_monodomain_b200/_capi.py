@@ -50,6 +50,9 @@ SYMBOLS = {
     "sphsm_stim_mesh": (C.c_int, [_H, _FP, C.c_int]),
     "sphsm_stim_cube": (C.c_int, [_H, _FP, C.c_int]),
     "sphsm_stim_off": (C.c_int, [_H]),
+    "sphsm_set_stim_box": (C.c_int, [_H, _FP, _FP, C.c_float]),
+    "sphsm_timer_mark": (C.c_int, [_H, C.c_int]),
+    "sphsm_timer_ms": (C.c_int, [_H, _FP]),
     "sphsm_set_masks": (C.c_int, [_H, _U8P, _FP, C.c_int]),
     "sphsm_step": (C.c_int, [_H, C.c_int]),
     "sphsm_stage": (C.c_int, [_H, C.c_int]),
@@ -57,6 +60,7 @@ SYMBOLS = {
     "sphsm_set_masks_async": (C.c_int, [_H, _U8P, _FP, C.c_int]),
     "sphsm_download_positions_async": (C.c_int, [_H, _FP, C.c_int]),
     "sphsm_download_owned_async": (C.c_int, [_H, _IP, _FP, C.c_int, _IP]),
+    "sphsm_set_stim_owned_async": (C.c_int, [_H, _FP, C.c_int]),
     "sphsm_io_wait": (C.c_int, [_H]),
     "sphsm_save_state": (C.c_int, [_H, C.c_char_p]),
     "sphsm_load_state": (C.c_int, [_H, C.c_char_p]),

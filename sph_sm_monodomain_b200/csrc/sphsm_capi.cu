@@ -112,7 +112,7 @@ struct sphsm_handle {
     bool stage_timing = false;
     double stage_time[7] = {0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[SPHSM_NUM_KERNEL_GROUPS + 2] = {};
-    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr;
+    cudaEvent_t ev_step0 = nullptr, ev_step1 = nullptr, ev_tm[2] = {nullptr, nullptr};
     float last_step_ms = 0.f;
     bool profiling = false;
     float group_ms[SPHSM_NUM_KERNEL_GROUPS] = {};
@@ -431,6 +431,8 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     for (auto &e : h->ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreate(&h->ev_step0));
     CU(cudaEventCreate(&h->ev_step1));
+    CU(cudaEventCreate(&h->ev_tm[0]));
+    CU(cudaEventCreate(&h->ev_tm[1]));
     *out = h;
     return SPHSM_OK;
 }
@@ -456,6 +458,7 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->ev_step0) cudaEventDestroy(h->ev_step0);
     if (h->ev_step1) cudaEventDestroy(h->ev_step1);
+    for (auto &e : h->ev_tm) if (e) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (auto &gx : h->graphs) cudaGraphExecDestroy(gx.exec);
@@ -674,6 +677,36 @@ __global__ void k_set_masks(const __grid_constant__ DevParams p, int n, Arrays a
     if (stim) a.E[s].w = stim[id];
 }
 
+// stim[k] for the k-th particle of the last owned-particle download (ids[k] as it was delivered; count = how many were).  A
+// particle that has left this rank since then is skipped: slot_of is validated against ID, and the slot must still be owned.
+__global__ void k_set_stim_owned(Arrays a, const int *__restrict__ ids, const float *__restrict__ stim, int count, const int *__restrict__ slot_of,
+                                 const int *__restrict__ rng, int first_h, int end_h) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int first = rng ? rng[0] : first_h, end = rng ? rng[1] : end_h;
+    const int id = ids[k];
+    if (id < 0) return;
+    const int s = slot_of[id];
+    if (s < first || s >= end || a.ID[s] != id) return;
+    a.E[s].w = stim[k];
+}
+// slot_of over the slots [rng[0], rng[1]) (device range) or [0, n)
+__global__ void k_slot_of_range(const int *__restrict__ rng, int n, int bound, const int *__restrict__ id, int *__restrict__ slot_of) {
+    const int first = rng ? rng[0] : 0, end = rng ? rng[1] : n;
+    const int s = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= end || s - first >= bound) return;
+    const int i = id[s];
+    if (i >= 0) slot_of[i] = s;
+}
+
+// set_stim for every particle inside an axis-aligned box (the O(N) form of turnOnStim_Cube's loop of set_stim calls, cpp:719-743)
+__global__ void k_set_stim_box(int n, Arrays a, float x0, float y0, float z0, float x1, float y1, float z1, float strength) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float4 q = a.P[s];
+    if (q.x >= x0 && q.x <= x1 && q.y >= y0 && q.y <= y1 && q.z >= z0 && q.z <= z1) a.E[s].w = strength;
+}
+
 // turnOffStim, cpp:764-783
 __global__ void k_stim_off(int n, Arrays a) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -873,12 +906,20 @@ extern "C" int sphsm_stim_cube(sphsm_handle *h, const float *xyz, int n) {
     return SPHSM_OK;
 }
 
+extern "C" int sphsm_set_stim_box(sphsm_handle *h, const float lo[3], const float hi[3], float strength) {
+    if (!h || !lo || !hi) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    const int n_k = h->dp.slab_on ? std::max(h->n_bound, h->n) : h->n;  // (dead slots hold NaN positions: never inside)
+    if (n_k > 0) LAUNCH(k_set_stim_box, cdiv(n_k, 256), 256, n_k, h->cur, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], strength);
+    CU(cudaGetLastError());
+    return SPHSM_OK;
+}
+
 extern "C" int sphsm_stim_off(sphsm_handle *h) {
     if (!h) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
-    int rc0 = slab_refresh(h);
-    if (rc0) return rc0;
-    if (h->n > 0) LAUNCH(k_stim_off, cdiv(h->n, 256), 256, h->n, h->cur);
+    const int n_k = h->dp.slab_on ? std::max(h->n_bound, h->n) : h->n;  // slab mode: the bound (dead slots are harmless to reset)
+    if (n_k > 0) LAUNCH(k_stim_off, cdiv(n_k, 256), 256, n_k, h->cur);
     CU(cudaGetLastError());
     return SPHSM_OK;
 }
@@ -955,6 +996,21 @@ extern "C" int sphsm_last_step_ms(sphsm_handle *h, float *ms) {
     CU(cudaEventSynchronize(h->ev_step1));
     CU(cudaEventElapsedTime(ms, h->ev_step0, h->ev_step1));
     h->last_step_ms = *ms;
+    return SPHSM_OK;
+}
+
+// a device-side stopwatch over any sequence of calls on this handle (bench.py: workloads whose timed region is more than one sphsm_step)
+extern "C" int sphsm_timer_mark(sphsm_handle *h, int which) {
+    if (!h || which < 0 || which > 1) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    CU(cudaEventRecord(h->ev_tm[which], h->stream));
+    return SPHSM_OK;
+}
+extern "C" int sphsm_timer_ms(sphsm_handle *h, float *ms) {
+    if (!h || !ms) return SPHSM_ERR_INVALID;
+    CU(cudaSetDevice(h->prm.device));
+    CU(cudaEventSynchronize(h->ev_tm[1]));
+    CU(cudaEventElapsedTime(ms, h->ev_tm[0], h->ev_tm[1]));
     return SPHSM_OK;
 }
 

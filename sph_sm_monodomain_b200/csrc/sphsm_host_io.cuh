@@ -172,6 +172,34 @@ extern "C" int sphsm_download_owned_async(sphsm_handle *h, int *ids, float *xyz,
     return SPHSM_OK;
 }
 
+// Per-step stimulation input for the particles a rank owns: stim[k] belongs to the k-th particle of the most recent
+// sphsm_download_owned_async on this handle (the device still holds that id list).  4 bytes per OWNED particle cross PCIe,
+// so the input traffic of a multi-GPU run does not grow with the number of ranks (sphsm_set_masks_async needs the global array
+// on every rank).  A particle that has migrated to a neighbour since that download keeps its previous value for one step.
+extern "C" int sphsm_set_stim_owned_async(sphsm_handle *h, const float *stim, int count) {
+    if (!h || !stim || count < 0) return SPHSM_ERR_INVALID;
+    if (count == 0) return SPHSM_OK;
+    if (!h->io_out_i || (size_t)count > h->io_out_cap) return fail(h, SPHSM_ERR_INVALID, "sphsm_set_stim_owned_async follows a sphsm_download_owned_async of at least `count` particles");
+    CU(cudaSetDevice(h->prm.device));
+    int rc;
+    if ((rc = ensure_io_in(h, (size_t)count)) != 0) return rc;
+    CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_in_free, 0));  // the previous call's kernel has consumed the staging
+    CU(cudaMemcpyAsync(h->io_in_f, stim, (size_t)count * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));
+    CU(cudaEventRecord(h->ev_in_ready, h->h2d_stream));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_in_ready, 0));
+    const bool slab = h->dp.slab_on != 0;
+    const int *rng = slab ? h->d_meta[h->meta_cur]->rng_all : nullptr;
+    const int bound = slab ? h->own_bound : h->n;
+    if (bound > 0) {
+        LAUNCH(k_slot_of_range, cdiv(bound, 256), 256, rng, h->n, bound, h->cur.ID, h->slot_of);
+        LAUNCH(k_set_stim_owned, cdiv(count, 256), 256, h->cur, (const int *)h->io_out_i, (const float *)h->io_in_f, count, (const int *)h->slot_of, rng, 0, h->n);
+        h->slot_of_valid = false;
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_in_free, h->stream));
+    return SPHSM_OK;
+}
+
 extern "C" int sphsm_io_wait(sphsm_handle *h) {
     if (!h) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));

@@ -131,6 +131,19 @@ class Sim:
         p = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
         self._ck(self.lib.sphsm_stim_cube(self.h, _fp(p), len(p)))
 
+    def set_stim_box(self, lo, hi, strength):
+        """set_stim for every particle inside the box [lo, hi] (sphsm_set_stim_box)."""
+        a, b = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+        self._ck(self.lib.sphsm_set_stim_box(self.h, _fp(a), _fp(b), float(strength)))
+
+    def timer_mark(self, which):
+        self._ck(self.lib.sphsm_timer_mark(self.h, int(which)))
+
+    def timer_ms(self):
+        v = C.c_float()
+        self._ck(self.lib.sphsm_timer_ms(self.h, C.byref(v)))
+        return v.value
+
     def turnOffStim(self):  # cpp:764-783
         self._ck(self.lib.sphsm_stim_off(self.h))
 

@@ -9,9 +9,23 @@ import pytest
 
 from oracle import CpuSim
 from tests.common import STAGE_OUT
-from tests.test_gpu_parity import TOL, assert_close
+from tests.test_gpu_parity import TOL, assert_close, field_scale
 
 pytestmark = pytest.mark.gpu
+
+# Steps after the first may contain DISCRETE events that rounding decides: a particle that lands within an ulp of a wall is
+# reflected (cpp:620-646: velocity sign flip) in one implementation and not in the other — on the jittered 1M lattice exactly one
+# particle does at step 2 (y = 8.887e-4 - 8.8875e-4; the fast path integrates with one FMA, the reference with a multiply and an
+# add).  It and the neighbours it then pushes are legitimate outliers of a trajectory comparison, so later steps bound the
+# NUMBER of particles beyond the tolerance (ten per million) instead of the maximum; step 1 has no such freedom.
+MAX_OUTLIER_FRACTION = 1e-5
+
+
+def per_particle_err(name, got, ref, params):
+    s = field_scale(name, ref, params)
+    g, r = got.astype(np.float64).reshape(len(got), -1), ref.astype(np.float64).reshape(len(ref), -1)
+    den = np.maximum(np.abs(r), s if s > 0 else 1e-30)
+    return (np.abs(g - r) / den).max(axis=1)
 
 CASES = {
     # name: (dims, quadratic, jitter, steps to compare at)
@@ -21,7 +35,7 @@ CASES = {
 }
 
 
-def acc_bound(got, want, consts, jitter):
+def acc_bound(got, want, consts, jitter, quantile=1.0):
     """Absolute bound on |acc - acc_ref|.  On a lattice near rest the acceleration is a cancelling sum, and its viscosity part
     multiplies velocity DIFFERENCES between neighbours by V * mu * Visco(r) / rho (cpp:559, 568) — ~3 per neighbour here — so it
     amplifies whatever (within-tolerance) difference the intermediate velocities carry (their own origin: the goal positions'
@@ -31,7 +45,8 @@ def acc_bound(got, want, consts, jitter):
     r_min = s * (1.0 - 2.0 * jitter)
     rho_min = float(want["dens"].min())
     coupling = 8 * (float(want["mass"].max()) / rho_min) * float(consts["mu"]) * float(consts["Spiky_constant"]) * (h - r_min) / rho_min
-    div = np.abs(got["inter_vel"].astype(np.float64) - want["inter_vel"]).max()
+    div = np.abs(got["inter_vel"].astype(np.float64) - want["inter_vel"]).max(axis=1)
+    div = float(div.max() if quantile >= 1.0 else np.quantile(div, quantile))
     return TOL * float(np.abs(want["acc"]).max()) + 2.0 * coupling * div
 
 
@@ -71,13 +86,22 @@ def test_fused_steps_at_scale(case, parity_record):
         assert np.array_equal(got["fixed"], want["fixed"]) and np.array_equal(got["stim"], want["stim"])
         for st in range(2, 8):
             for f in STAGE_OUT[st]:
+                tol = tol_for(f, quadratic, target)
+                if target > 1:  # (see MAX_OUTLIER_FRACTION)
+                    e = per_particle_err(f, got[f], want[f], params) if f != "acc" else np.abs(got["acc"].astype(np.float64) - want["acc"]).max(axis=1)
+                    lim = tol if f != "acc" else acc_bound(got, want, c, jitter, quantile=1.0 - MAX_OUTLIER_FRACTION)
+                    frac = float((e > lim).mean())
+                    typical = float(np.quantile(e, 1.0 - MAX_OUTLIER_FRACTION))
+                    parity_record("fused_steps_at_scale", f"{case}/step{target}", f + " (all but 1e-5 of the particles)", typical, lim)
+                    parity_record("fused_steps_at_scale", f"{case}/step{target}", f + " (fraction of particles beyond the tolerance)", frac, MAX_OUTLIER_FRACTION)
+                    assert frac <= MAX_OUTLIER_FRACTION, (f, frac, float(e.max()))
+                    continue
                 if f == "acc":
                     bound = acc_bound(got, want, c, jitter)
                     dacc = float(np.abs(got["acc"].astype(np.float64) - want["acc"]).max())
                     parity_record("fused_steps_at_scale", f"{case}/step{target}", "acc (absolute; bound = what the velocity differences imply)", dacc, bound)
                     assert dacc <= bound, (dacc, bound)
                     continue
-                tol = tol_for(f, quadratic, target)
                 err = assert_close(f, got[f], want[f], params, tol=tol)
                 parity_record("fused_steps_at_scale", f"{case}/step{target}", f, err, tol)
     ora.close()

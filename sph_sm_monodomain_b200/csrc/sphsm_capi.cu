@@ -139,6 +139,12 @@ struct sphsm_handle {
     int n_bound = 0;                       // upper bound of the live slot count the grids of the slab step are sized for
     int own_bound = 0;                     // likewise for the owned slots
     int *d_count = nullptr;                // sphsm_download_owned_async: the owned count of the queued gather
+    // exchange 1 of the NEXT step issued at the end of a step, behind pass B on the outer planes (it travels while the interior
+    // planes are still being integrated).  Anything that changes particle state other than stimulation values between two steps
+    // voids it (x1_early_valid = false): the next step then classifies and exchanges again, on every rank alike — state mutators
+    // are collective calls in slab mode.
+    bool x1_early_pending = false, x1_early_valid = false;
+    cudaEvent_t ev_x1 = nullptr;
     int b2 = 0, b3 = 0;       // start of the 2nd / of the last owned plane, as of the last applied read-back
     int n_global = 0;         // particles uploaded before sphsm_comm_set_slab filtered them (ids are global)
     int mom_n = 0;            // slab step: extent of the PRE-reorder arrays (old slots + both message regions) the REST-state sums scan
@@ -399,6 +405,7 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&h->ev_in_ready, &h->ev_in_free, &h->ev_out_ready, &h->ev_out_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_x1, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming));
     h->launch_stream = h->stream;
     if ((rc = alloc_arrays(h, h->cur, cap, true)) != 0) return rc;
@@ -470,6 +477,7 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
     cudaFree(h->io_in_f); cudaFree(h->io_in_b); cudaFree(h->io_out_f); cudaFree(h->io_out_i);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
+    if (h->ev_x1) cudaEventDestroy(h->ev_x1);
     if (h->ev_int) cudaEventDestroy(h->ev_int);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -753,6 +761,7 @@ static void state_changed(sphsm_handle *h, bool rest) {
     h->slot_of_valid = false;
     h->inter_live = true;
     h->prev_vel_valid = false;
+    h->x1_early_valid = false;
     if (rest) {
         h->goal_pv_stale = false;  // uploads / Init_Fluid write GOAL, PV and their frozen copies
         h->rest_dirty = true;
@@ -880,6 +889,7 @@ extern "C" int sphsm_set_stim(sphsm_handle *h, float cx, float cy, float cz, flo
 extern "C" int sphsm_stim_mesh(sphsm_handle *h, const float *xyz, int n) {
     if (!h || (!xyz && n > 0)) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
+    h->x1_early_valid = false;
     int rc = stim_list(h, xyz, n, 0.01f, h->prm.stim_strength);  // cpp:753
     if (rc) return rc;
     if (h->n > 0) LAUNCH(k_fix_rule, cdiv(h->n, 256), 256, h->dp, h->n, h->cur, 0, freeze_source(h));
@@ -898,6 +908,7 @@ extern "C" int sphsm_stim_cube(sphsm_handle *h, const float *xyz, int n) {
             sel.push_back(px); sel.push_back(xyz[3 * i + 1]); sel.push_back(pz);
         }
     }
+    h->x1_early_valid = false;
     int rc = stim_list(h, sel.data(), (int)(sel.size() / 3), 0.001f, h->prm.stim_strength);  // cpp:728
     if (rc) return rc;
     if (h->n > 0) LAUNCH(k_fix_rule, cdiv(h->n, 256), 256, h->dp, h->n, h->cur, 1, freeze_source(h));
@@ -918,6 +929,7 @@ extern "C" int sphsm_set_stim_box(sphsm_handle *h, const float lo[3], const floa
 extern "C" int sphsm_stim_off(sphsm_handle *h) {
     if (!h) return SPHSM_ERR_INVALID;
     CU(cudaSetDevice(h->prm.device));
+    h->x1_early_valid = false;  // (Vm of the halo copies already sent would be stale)
     const int n_k = h->dp.slab_on ? std::max(h->n_bound, h->n) : h->n;  // slab mode: the bound (dead slots are harmless to reset)
     if (n_k > 0) LAUNCH(k_stim_off, cdiv(n_k, 256), 256, n_k, h->cur);
     CU(cudaGetLastError());
@@ -930,6 +942,7 @@ extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const floa
     if (n == 0 || (!fixed && !stim)) return SPHSM_OK;
     CU(cudaSetDevice(h->prm.device));
     int rc;
+    h->x1_early_valid = false;
     if ((rc = slab_refresh(h)) != 0) return rc;
     if ((rc = ensure_tmp(h, (size_t)n)) != 0) return rc;
     if ((rc = ensure_itmp(h, (size_t)(n + 3) / 4)) != 0) return rc;

@@ -35,8 +35,11 @@ struct SlabMeta {
     int rng_int[4];    //   the interior planes [b2, b3)
     int rng_bnd[4];    //   the two boundary planes: [own_begin, own_end) minus the hole [b2, b3)
     int bound_viol;    // live slots exceeded the grid bound the host launched with
-    int pad[11];
+    int rng_int2[4];   //   the planes at least two planes away from both faces
+    int rng_bnd2[4];   //   the two outermost owned planes on either side (everything an exchange-1 message can come from)
+    int pad[3];
 };
+static_assert(sizeof(SlabMeta) == 128, "SlabMeta is 32 ints");
 
 // one message = [count, pad x3] [P x cap] [VEL x cap] [O x cap] [E x cap] [ID x cap]
 struct MsgView {
@@ -115,6 +118,47 @@ __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ Dev
     }
 }
 
+// The same selection over a launch range (rng = {begin, end, hole_begin, hole_len} in device memory) with the positions given
+// explicitly: run right after pass B on the two outermost planes of either side, on the freshly integrated positions `Pnew`,
+// so that exchange 1 of the NEXT step travels while pass B still works on the interior planes.
+__global__ void __launch_bounds__(256) k_mg_classify_rng(const __grid_constant__ DevParams p, Arrays a, const float4 *__restrict__ Pnew,
+                                                         const int *__restrict__ rng, int has_left, int has_right, MsgView L, MsgView R, int cap,
+                                                         int *err) {
+    const int4 r = *reinterpret_cast<const int4 *>(rng);
+    int s = r.x + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= r.z) s += r.w;
+    if (s >= r.y) return;
+    const float4 q = Pnew[s];
+    const int pl = slab_plane(p, q);
+    if ((has_left && pl < p.slab_lo - 1) || (has_right && pl > p.slab_hi) || pl == INT_MIN) atomicAdd(&err[0], 1);
+    if (has_left && pl <= p.slab_lo) {
+        const int k = atomicAdd(L.count, 1);
+        if (k < cap) msg_put(L, k, a, s, q);
+        else atomicAdd(&err[1], 1);
+    }
+    if (has_right && pl >= p.slab_hi - 1) {
+        const int k = atomicAdd(R.count, 1);
+        if (k < cap) msg_put(R, k, a, s, q);
+        else atomicAdd(&err[1], 1);
+    }
+}
+// what is left of k_mg_classify at the start of the next step when its exchange has already happened: last step's halo copies
+// are dropped, and an interior particle that now sits where it should have been sent (it crossed two planes) is an error
+__global__ void __launch_bounds__(256) k_mg_drop_halos(Arrays a, const SlabMeta *__restrict__ m, int cap) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 2 * cap) return;
+    const int side = idx >= cap, k = idx - side * cap;
+    const int first = side ? m->own_end : 0, cnt = side ? m->n_live - m->own_end : m->own_begin;
+    if (k < cnt) a.P[first + k].x = __int_as_float(0x7fc00000);
+}
+__global__ void __launch_bounds__(256) k_mg_check_interior(const __grid_constant__ DevParams p, const float4 *__restrict__ P, const SlabMeta *__restrict__ m,
+                                                           int has_left, int has_right, int *err) {
+    const int s = m->rng_int2[0] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m->rng_int2[1]) return;
+    const int pl = slab_plane(p, P[s]);
+    if ((has_left && pl <= p.slab_lo) || (has_right && pl >= p.slab_hi - 1) || pl == INT_MIN) atomicAdd(&err[0], 1);
+}
+
 // arrivals -> slots [n0, n0 + 2*cap), n0 = the live count before this step's exchange: left message first; unused slots are dead.
 // A message whose header count exceeds the capacity was truncated by its sender: the receiver flags it in the same step.
 __global__ void __launch_bounds__(256) k_mg_unpack(const SlabMeta *__restrict__ prev, Arrays a, int has_left, int has_right, MsgView L, MsgView R,
@@ -164,6 +208,12 @@ __global__ void k_mg_meta(const int *__restrict__ cell_start, int num_cells, int
     m->rng_int[0] = b2; m->rng_int[1] = three ? b3 : b2; m->rng_int[2] = 0; m->rng_int[3] = 0;
     m->rng_bnd[0] = ob; m->rng_bnd[1] = oe; m->rng_bnd[2] = three ? b2 : 0; m->rng_bnd[3] = three ? b3 - b2 : 0;
     m->bound_viol = n > n_bound ? 1 : 0;
+    // two planes per side (a particle moves at most one plane per step, so whatever must be sent to a neighbour after the step
+    // sits in one of them): [own_begin, p2) and [p3, own_end), p2 / p3 = start of the 3rd / of the last-but-one owned plane
+    const int p2 = cell_start[plane_cells * min(3, gcl - 1)], p3 = cell_start[plane_cells * max(gcl - 3, 1)];
+    const bool five = gcl - 2 >= 5 && p3 > p2;
+    m->rng_int2[0] = p2; m->rng_int2[1] = five ? p3 : p2; m->rng_int2[2] = 0; m->rng_int2[3] = 0;
+    m->rng_bnd2[0] = ob; m->rng_bnd2[1] = oe; m->rng_bnd2[2] = five ? p2 : 0; m->rng_bnd2[3] = five ? p3 - p2 : 0;
 }
 
 // exchange 2, sender side: pass A's records (V = inter_vel + m/dens, S = pres + dens) of the first owned plane go to the left
@@ -183,9 +233,12 @@ __global__ void __launch_bounds__(256) k_mg_pack2(const SlabMeta *__restrict__ m
 }
 // receiver side: the left halo plane is slots [0, own_begin), the right one [own_end, n_live); both sides of a face hold the
 // shared plane in the same (canonical) order.  A population that differs from the sender's is an error (err[1]).
+// zero0 / zero1: the headers of the two SEND buffers (free again: this kernel runs behind exchange 2), cleared for the early
+// exchange-1 packing that may follow
 __global__ void __launch_bounds__(256) k_mg_unpack2(const SlabMeta *__restrict__ m, Arrays a, int has_left, int has_right, Msg2View L, Msg2View R,
-                                                    int cap, int *err) {
+                                                    int cap, int *err, int *zero0, int *zero1) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) { *zero0 = 0; *zero1 = 0; }
     if (idx >= 2 * cap) return;
     const int side = idx >= cap, k = idx - side * cap;
     if (side ? !has_right : !has_left) return;

@@ -97,6 +97,7 @@ extern "C" int sphsm_set_masks_async(sphsm_handle *h, const uint8_t *fixed, cons
     if (n == 0 || (!fixed && !stim)) return SPHSM_OK;
     CU(cudaSetDevice(h->prm.device));
     int rc;
+    h->x1_early_valid = false;
     if ((rc = ensure_io_in(h, (size_t)n)) != 0) return rc;
     CU(cudaStreamWaitEvent(h->h2d_stream, h->ev_in_free, 0));  // the previous call's kernel has consumed the staging
     if (stim) CU(cudaMemcpyAsync(h->io_in_f, stim, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->h2d_stream));

@@ -205,6 +205,7 @@ extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
     if ((rc = setup_grid_buffers(h)) != 0) return rc;
     // keep only the owned planes: dead entries sort into the limbo bucket and fall off the end
     h->local_error = 0; h->peer_error = false; h->failed = false;
+    h->x1_early_pending = false; h->x1_early_valid = false;
     h->meta_consumed = h->meta_issued;  // (read-backs of an earlier slab are void)
     if (h->d_err) CU(cudaMemsetAsync(h->d_err, 0, 4 * sizeof(int), h->stream));
     h->n_bound = h->alloc_n;
@@ -256,16 +257,16 @@ static int comm_allreduce(sphsm_handle *h, int count) {
     NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm_red, h->launch_stream));
     return SPHSM_OK;
 }
-static int nccl_exchange1(sphsm_handle *h) {
+static int nccl_exchange1(sphsm_handle *h, cudaStream_t st) {
     const size_t bytes = msg_bytes(h->send_cap);
     NC(g_nccl.GroupStart());
     if (h->rank > 0) {
-        NC(g_nccl.Send(h->msg_send[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(h->msg_recv[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Send(h->msg_send[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->msg_recv[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, st));
     }
     if (h->rank < h->nranks - 1) {
-        NC(g_nccl.Send(h->msg_send[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(h->msg_recv[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Send(h->msg_send[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->msg_recv[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, st));
     }
     NC(g_nccl.GroupEnd());
     return SPHSM_OK;
@@ -296,13 +297,14 @@ static int pack2(sphsm_handle *h) {
 static int unpack2(sphsm_handle *h) {
     const int cap = h->send_cap;
     LAUNCH(k_mg_unpack2, cdiv(2 * cap, 256), 256, h->d_meta[h->meta_cur], h->cur, h->rank > 0 ? 1 : 0, h->rank < h->nranks - 1 ? 1 : 0,
-           msg2_view(h->msg_recv[0], cap), msg2_view(h->msg_recv[1], cap), cap, h->d_err);
+           msg2_view(h->msg_recv[0], cap), msg2_view(h->msg_recv[1], cap), cap, h->d_err, reinterpret_cast<int *>(h->msg_send[0]),
+           reinterpret_cast<int *>(h->msg_send[1]));
     return SPHSM_OK;
 }
 
 // ---- the slab step as phases; every phase ends in the collective named by *coll ----------------------------------------
-enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE, COLL_ALLREDUCE_MOMENTS };
-static const int MG_PHASES = 6;
+enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE, COLL_ALLREDUCE_MOMENTS, COLL_EXCH1_TAKEN, COLL_EXCH1_EARLY };
+static const int MG_PHASES = 7;
 
 static int mg_forked_allreduce(sphsm_handle *h);
 // `sync_meta`: the host waits for the plane boundaries in every step (virtual ranks, profiling, the first step after the
@@ -343,6 +345,29 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                     h->allreduce_pending = false;
                 }
             }
+            if (h->x1_early_pending && h->x1_early_valid) {
+                // exchange 1 of this step left at the end of the previous one (phase 5): only the stale halo copies have to go,
+                // and nothing in the interior may sit where it should have been sent from (checked beside the sums)
+                h->x1_early_pending = false;
+                LAUNCH(k_mg_drop_halos, cdiv(2 * cap, 256), 256, h->cur, h->d_meta[h->meta_cur], cap);
+                h->launch_stream = h->side_stream;
+                rc = [&]() -> int {
+                    if (!h->moments_forked) {  // (the side stream is not forked in this step: order it behind the main stream first)
+                        CU(cudaEventRecord(h->ev_fork, h->stream));
+                        CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+                    }
+                    LAUNCH(k_mg_check_interior, cdiv(std::max(h->own_bound, 1), 256), 256, h->dp, h->cur.P, h->d_meta[h->meta_cur], has_left ? 1 : 0,
+                           has_right ? 1 : 0, h->d_err);
+                    return SPHSM_OK;
+                }();
+                h->launch_stream = h->stream;
+                if (rc) return rc;
+                CU(cudaStreamWaitEvent(h->stream, h->ev_x1, 0));
+                if (h->gt) h->gt->end_group(KG_OTHER);
+                *coll = COLL_EXCH1_TAKEN;
+                return SPHSM_OK;
+            }
+            h->x1_early_pending = false;  // (voided by a mutator: the messages are packed and exchanged again, on every rank alike)
             CU(cudaMemsetAsync(h->msg_send[0], 0, 16, h->stream));
             CU(cudaMemsetAsync(h->msg_send[1], 0, 16, h->stream));
             LAUNCH(k_mg_classify, cdiv(std::max(h->n_bound, 1), 256), 256, h->dp, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_send[0], cap),
@@ -431,8 +456,9 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 CU(cudaEventRecord(h->ev_bnd, h->side_stream));
                 if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_int)) != 0) return rc;  // (queued before the NCCL calls: they take host time)
                 CU(cudaEventRecord(h->ev_int, h->stream));
-                CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
-                if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_int)) != 0) return rc;
+                // pass B is cut two planes deep: the planes at least two away from a face read no boundary-plane record at all, so
+                // they follow pass A's interior directly; the two outer planes of either side wait for exchange 2 on the side stream
+                if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_int2)) != 0) return rc;
                 if (g_host_prof_early() && h->pev[4]) CU(cudaEventRecord(h->pev[4], h->side_stream));
                 rc = nccl_exchange2(h, h->side_stream);
                 if (g_host_prof_early() && h->pev[5]) CU(cudaEventRecord(h->pev[5], h->side_stream));
@@ -447,18 +473,31 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
         case 5: {  // pass B on the owned slots
             if (h->gt) h->gt->end_group(KG_OTHER);  // exchange 2
             const SlabMeta *m = h->d_meta[h->meta_cur];
-            if (h->split) {  // interior planes need no halo record; the boundary planes wait for exchange 2 (stream order)
-                CU(cudaStreamWaitEvent(h->side_stream, h->ev_int, 0));  // (pass B's interior was queued in phase 4)
+            if (h->split) {  // the outer planes wait for exchange 2 (stream order) and for pass A's interior (ev_int)
+                CU(cudaStreamWaitEvent(h->side_stream, h->ev_int, 0));
                 h->launch_stream = h->side_stream;
                 rc = unpack2(h);
-                if (!rc) rc = launch_pass_b(h, 0, 2 * cap, diag, 0, 0, false, m->rng_bnd);
+                if (!rc) rc = launch_pass_b(h, 0, 4 * cap, diag, 0, 0, false, m->rng_bnd2);
+                // their new positions decide what the neighbours get next step: pack it now and let exchange 1 travel while the
+                // main stream is still busy with the inner planes
+                if (!rc) rc = [&]() -> int {
+                    LAUNCH(k_mg_classify_rng, cdiv(4 * cap, 256), 256, h->dp, h->cur, (const float4 *)h->alt.P, m->rng_bnd2, has_left ? 1 : 0, has_right ? 1 : 0,
+                           msg_view(h->msg_send[0], cap), msg_view(h->msg_send[1], cap), cap, h->d_err);
+                    return SPHSM_OK;
+                }();
                 h->launch_stream = h->stream;
                 if (rc) return rc;
+                *coll = COLL_EXCH1_EARLY;
+                return SPHSM_OK;
+            }
+            if ((rc = unpack2(h)) != 0) return rc;
+            if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_all)) != 0) return rc;
+            return SPHSM_OK;
+        }
+        case 6: {  // the two streams meet; bookkeeping
+            if (h->split) {
                 CU(cudaEventRecord(h->ev_join, h->side_stream));
                 CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-            } else {
-                if ((rc = unpack2(h)) != 0) return rc;
-                if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_all)) != 0) return rc;
             }
             std::swap(h->cur.P, h->alt.P);
             if (h->gt) {
@@ -520,12 +559,21 @@ static int mg_step_nccl(sphsm_handle *h) {
                     if (!h->pev[k]) CU(cudaEventCreate(&h->pev[k]));
                 CU(cudaEventRecord(h->pev[0], h->stream));
             }
-            rc = nccl_exchange1(h);
+            rc = nccl_exchange1(h, h->stream);
             if (g_host_prof) CU(cudaEventRecord(h->pev[1], h->stream));
             if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[2], h->side_stream));
             if (!rc && h->moments_forked && h->allreduce_pending) rc = mg_forked_allreduce(h);
             h->allreduce_pending = false;
             if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[3], h->side_stream));
+        }
+        else if (coll == COLL_EXCH1_TAKEN) {  // the exchange happened at the end of the previous step: only the allreduce is left
+            if (h->moments_forked && h->allreduce_pending) rc = mg_forked_allreduce(h);
+            h->allreduce_pending = false;
+        } else if (coll == COLL_EXCH1_EARLY) {  // next step's exchange 1, on the side stream behind the outer planes' pass B
+            rc = nccl_exchange1(h, h->side_stream);
+            if (!rc) CU(cudaEventRecord(h->ev_x1, h->side_stream));
+            h->x1_early_pending = true;
+            h->x1_early_valid = true;
         }
         else if (coll == COLL_ALLREDUCE) rc = comm_allreduce(h, count);
         else if (coll == COLL_ALLREDUCE_MOMENTS) rc = moment_allreduce(h);

@@ -12,8 +12,10 @@
 //   * Get_Paticles() returns a host mirror that is refreshed lazily from the device; writes made through the pointer
 //     are detected (compared with a shadow copy) and uploaded before the next device operation — see
 //     set_accessor_readonly() to skip that check on large particle counts;
-//   * the d_* stage timers hold DEVICE time (CUDA events), filled while stage timing is on (default, like the
-//     reference); set_stage_timing(false) switches Animation() to the fused 2-pass step.
+//   * Animation() runs the fused two-pass step; the d_* stage timers hold DEVICE time (CUDA events) sampled from every 50th
+//     step and filed under the stage that dominates each kernel group (find_neighbors, corrected_velocity,
+//     intermediate_velocity = pass A, compute_Force = pass B); set_stage_timing(true) (or SPHSM_STAGE_TIMING=1) runs the
+//     reference's seven stages one kernel group each, with an event pair around every one, as the reference times them.
 #ifndef __SPH_SM_monodomain_H__
 #define __SPH_SM_monodomain_H__
 
@@ -135,7 +137,7 @@ public:
 
     // ---- extensions (no reference counterpart) ----------------------------------------------------------------
     void Animation(int nsteps);                 // nsteps steps with one call (asynchronous on the device stream)
-    void set_stage_timing(bool on);             // false: fused step, d_* no longer advance
+    void set_stage_timing(bool on);             // true: the seven stages run and are timed one by one (default: fused step, sampled timers)
     void set_accessor_readonly(bool on);        // true: Get_Paticles() results are never written back
     const Particle *Get_Paticles_readonly();    // refresh + return without arming the write-back check
     void download_positions(float *xyz);        // 3 floats per particle, what a viewer needs each frame

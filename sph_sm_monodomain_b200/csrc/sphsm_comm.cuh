@@ -15,6 +15,7 @@
 //   exchange 2      after pass A the boundary planes' V / S records travel as contiguous slot ranges
 #pragma once
 #include <limits.h>
+#include <stddef.h>
 
 #include "sphsm_types.cuh"
 
@@ -34,11 +35,12 @@ struct SlabMeta {
     int rng_all[4];    // launch ranges {begin, end, hole_begin, hole_len}: every owned slot
     int rng_int[4];    //   the interior planes [b2, b3)
     int rng_bnd[4];    //   the two boundary planes: [own_begin, own_end) minus the hole [b2, b3)
-    int bound_viol;    // live slots exceeded the grid bound the host launched with
     int rng_int2[4];   //   the planes at least two planes away from both faces
     int rng_bnd2[4];   //   the two outermost owned planes on either side (everything an exchange-1 message can come from)
-    int pad[3];
+    int bound_viol;    // live slots exceeded the grid bound the host launched with
+    int pad[3];        // (the ranges are read as int4: every one of them sits on a 16-byte boundary)
 };
+static_assert(offsetof(SlabMeta, rng_all) % 16 == 0 && offsetof(SlabMeta, rng_int2) % 16 == 0 && offsetof(SlabMeta, rng_bnd2) % 16 == 0, "int4 loads");
 static_assert(sizeof(SlabMeta) == 128, "SlabMeta is 32 ints");
 
 // one message = [count, pad x3] [P x cap] [VEL x cap] [O x cap] [E x cap] [ID x cap]

@@ -7,6 +7,7 @@
 // to continue on.
 #include <SPH_SM_monodomain.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -67,11 +68,14 @@ void SPH_SM_monodomain::construct(int capacity, m3Vector world) {
     mirror_handed_out = false;
     accessor_readonly = false;
     cells_current = false;
-    stage_timing = true;
+    // Animation() runs the fused step (two neighbour passes, CUDA-graph replay on small sets).  The d_* timers of the reference
+    // (h:97-99) are fed by SAMPLING: every SAMPLE_PERIOD-th step runs with per-kernel-group CUDA events and stands for the
+    // period (see Animation); set_stage_timing(true) switches to the reference's seven separately timed stages instead.
+    stage_timing = getenv("SPHSM_STAGE_TIMING") && atoi(getenv("SPHSM_STAGE_TIMING")) != 0;
     for (int k = 0; k < 7; k++) stage_seen[k] = 0.0;
     d_find_neighbors = d_corrected_velocity = d_intermediate_velocity = d_Density_SingPressure = d_cell_model = d_compute_Force =
         d_Update_Properties = duration_d::zero();
-    must(dev, sphsm_enable_stage_timing(dev, 1), "sphsm_enable_stage_timing");
+    must(dev, sphsm_enable_stage_timing(dev, stage_timing ? 1 : 0), "sphsm_enable_stage_timing");
 
     // the reference's banner, cpp:71-78 (it prints Grid_Size.y on the Z line too)
     cout << "SPHSystem" << endl;
@@ -316,12 +320,41 @@ void SPH_SM_monodomain::collect_stage_times() {
     }
 }
 
+// Fused step: the kernel groups do not map one to one onto the reference's seven stages, so the sampled group times land in
+// the slot of the stage that dominates each group: neighbour grid (hash + sort + gather) -> d_find_neighbors; shape-matching
+// sums + solve (+ goal / corrected velocity, applied inside the gather) -> d_corrected_velocity; pass A (intermediate velocity
+// AND density / pressure in one sweep) -> d_intermediate_velocity; pass B (cell model + force + Laplacian + integration)
+// -> d_compute_Force; d_Density_SingPressure, d_cell_model and d_Update_Properties stay zero.
+static const int SAMPLE_PERIOD = 50;
 void SPH_SM_monodomain::Animation(int nsteps) {
     push_host_writes();
-    must(dev, sphsm_step(dev, nsteps), "sphsm_step");
-    total_time_steps += nsteps;
+    if (stage_timing) {
+        must(dev, sphsm_step(dev, nsteps), "sphsm_step");
+        total_time_steps += nsteps;
+        device_changed();
+        collect_stage_times();
+        return;
+    }
+    int left = nsteps;
+    while (left > 0) {
+        if (total_time_steps % SAMPLE_PERIOD == 0) {  // a sampled step: per-group CUDA events, weighted for the whole period
+            float ms[SPHSM_NUM_KERNEL_GROUPS];
+            must(dev, sphsm_profile_step(dev, 1, ms), "sphsm_profile_step");
+            const double w = 1e-3 * SAMPLE_PERIOD;
+            d_find_neighbors += duration_d(w * (ms[0] + ms[1] + ms[2]));
+            d_corrected_velocity += duration_d(w * (ms[3] + ms[4]));
+            d_intermediate_velocity += duration_d(w * ms[5]);
+            d_compute_Force += duration_d(w * ms[6]);
+            total_time_steps += 1;
+            left -= 1;
+            continue;
+        }
+        const int run = std::min(left, SAMPLE_PERIOD - total_time_steps % SAMPLE_PERIOD);
+        must(dev, sphsm_step(dev, run), "sphsm_step");
+        total_time_steps += run;
+        left -= run;
+    }
     device_changed();
-    if (stage_timing) collect_stage_times();
 }
 void SPH_SM_monodomain::compute_SPH_SM_monodomain() { Animation(1); }  // cpp:794-824
 void SPH_SM_monodomain::Animation() { Animation(1); }                  // cpp:826-829
@@ -329,7 +362,8 @@ void SPH_SM_monodomain::Animation() { Animation(1); }                  // cpp:82
 void SPH_SM_monodomain::print_report(double avg_fps, double avg_step_d) {  // the 23-field line of cpp:785-792
     sphsm_params p;
     must(dev, sphsm_get_params(dev, &p), "sphsm_get_params");
-    const double n = (double)total_time_steps;
+    // (sampled timers cover whole periods: normalise by the steps they stand for)
+    const double n = stage_timing ? (double)total_time_steps : (double)(((total_time_steps + SAMPLE_PERIOD - 1) / SAMPLE_PERIOD) * SAMPLE_PERIOD);
     cout << avg_fps << ";" << avg_step_d << ";" << total_time_steps;
     const duration_d *slots[7] = {&d_find_neighbors,       &d_corrected_velocity, &d_intermediate_velocity, &d_Density_SingPressure,
                                   &d_cell_model,           &d_compute_Force,      &d_Update_Properties};

@@ -58,7 +58,7 @@ static void cube_positions(vector<m3Vector> &out) {
 
 int main(int argc, char **argv) {
     std::string csv, xyz, dump;
-    bool cube = false, stim_off = true, quadratic = false, fused = false;
+    bool cube = false, stim_off = true, quadratic = false, fused = false, staged = false;
     int steps = 500, subsample = 0, frame_every = 1, capacity = 0;
     float world[3] = {1.5f, 1.5f, 1.5f};
     for (int a = 1; a < argc; a++) {
@@ -74,7 +74,8 @@ int main(int argc, char **argv) {
         else if (s == "--world" && a + 3 < argc) { for (int k = 0; k < 3; k++) world[k] = (float)atof(argv[++a]); }
         else if (s == "--no-stim-off") stim_off = false;
         else if (s == "--quadratic") quadratic = true;
-        else if (s == "--fused") fused = true;
+        else if (s == "--fused") fused = true;    // (the default since round 2; kept for old command lines)
+        else if (s == "--staged") staged = true;  // the reference's seven separately timed stages
         else { fprintf(stderr, "unknown argument %s\n", s.c_str()); return 2; }
     }
 
@@ -90,6 +91,7 @@ int main(int argc, char **argv) {
     else sph->turnOnStim_Mesh(positions);       // init_mesh, main.cpp:486-487
     if (quadratic) sph->flip_quadratic();
     if (fused) sph->set_stage_timing(false);
+    if (staged) sph->set_stage_timing(true);
 
     duration_d stepping(0);
     double displacement_sum = 0.0;  // what display_points consumes; keeps the accessor honest

@@ -104,6 +104,7 @@ int main(int argc, char **argv) {
             std::cout << "Turning stimulation off" << std::endl;
         }
         sph->Animation();
+        sph->synchronize();  // the reference's step is synchronous: time the work, not the launch
         stepping += std::chrono::system_clock::now() - t0;
         if (frame_every > 0 && (steps - left) % frame_every == 0) {  // display(): Get_Paticles() + per-particle reads
             Particle *p = sph->Get_Paticles();

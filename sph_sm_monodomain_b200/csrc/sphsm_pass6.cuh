@@ -86,6 +86,7 @@ template <int T, bool WITH4>
 struct Lay6 {
     static constexpr int SLOTS = 14 * T;  // 16-byte records staged per block: a lattice block needs 9-16 lattice lines of ~T + 4
     static constexpr int SLOTS4 = SLOTS + 9 * 8;
+    static constexpr int LISTK = LIST_K;  // in-range list entries per lane between drains
     static constexpr unsigned OFF_MBAR = 0, OFF_C16 = 16, OFF_C4 = 52, OFF_FLAG = 96, OFF_LIST = 128;
     static constexpr unsigned OFF_ST16 = OFF_LIST + 4u * LIST_K * T;
     static constexpr unsigned OFF_ST4 = OFF_ST16 + 16u * SLOTS;
@@ -158,13 +159,13 @@ __device__ __forceinline__ bool stage_spans6(const DevParams &p, const int *__re
 }
 
 // Sweep the nine stencil rows in the reference's order (cpp:462-464), as sweep4 does; `row(r)` is called before each row with its
-// index (plane-major), so that the staged variant can fetch the row's shared-memory address constants.
-template <int T, int STEP, class Row, class Pair, class One, class Drain>
+// plane (0..2) and row (0..2) indices, so that the staged variant can fetch the row's shared-memory address constants.
+template <int T, int STEP, int LISTK, class Row, class Pair, class One, class Drain>
 __device__ __forceinline__ void sweep6(const int *__restrict__ cell_start, const int ga, const int gagb, const int num_cells, const int key,
                                        const unsigned lbase, unsigned &lofs, Row &&row, Pair &&pair, One &&one, Drain &&drain) {
     constexpr unsigned LSTEP6 = 4u * T;
     const int *center = cell_start + (key - 1);
-    const unsigned lmax = lbase + LIST_K * LSTEP6;
+    const unsigned lmax = lbase + LISTK * LSTEP6;
     Rows3 cur, nxt;
     load_rows3(center - gagb, ga, key >= gagb, cur);
 #pragma unroll 1
@@ -175,7 +176,7 @@ __device__ __forceinline__ void sweep6(const int *__restrict__ cell_start, const
         for (int k = 0; k < 3; k++) {
             int j = cur.s[k];
             const int e = cur.e[k];
-            row(3 * dc + k);
+            row(dc, k);
             if (lofs + (unsigned)(e - j) * LSTEP6 <= lmax) {
 #pragma unroll 1
                 for (; j < e; j += STEP) pair(j, e, lofs);  // the body masks j+1 .. j+STEP-1 against the row end itself
@@ -195,11 +196,13 @@ __device__ __forceinline__ void sweep6(const int *__restrict__ cell_start, const
 
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
-template <int T, bool STAGED>
+// L = the shared-memory layout; tstride / trow: the address tables hold `tstride` spans per plane and this target's three stencil
+// rows are entries trow, trow + 1, trow + 2 of each plane (generation 6: 3 and 0; the multi-row tiles of generation 7: R + 2 and
+// the target's row inside the tile)
+template <class L, int T, bool STAGED>
 __device__ __forceinline__ void pass_a6_neighbours(const DevParams *__restrict__ g, const Arrays &a, const int *__restrict__ cell_start, const int key,
-                                                   const unsigned smem0, const float4 pi, const float4 ci, float &dens, float &pvx, float &pvy,
-                                                   float &pvz) {
-    using L = Lay6<T, false>;
+                                                   const unsigned smem0, const int tstride, const int trow, const float4 pi, const float4 ci,
+                                                   float &dens, float &pvx, float &pvy, float &pvz) {
     constexpr unsigned LSTEP6 = 4u * T;
     const int z0 = g->zero;  // == 0, loaded from global: what is derived from it stays in registers (see list_put)
     const float4 *__restrict__ P = pinned(a.P, z0);
@@ -207,7 +210,7 @@ __device__ __forceinline__ void pass_a6_neighbours(const DevParams *__restrict__
     const float h2 = g->h2, c6 = g->c_poly6;
     const int ga = g->ga, gagb = g->ga * g->gb, num_cells = g->num_cells;
     const unsigned lbase = smem0 + L::OFF_LIST + 4u * (unsigned)(threadIdx.x + z0);
-    const unsigned tab = smem0 + L::OFF_C16 + (unsigned)z0;
+    const unsigned tab = smem0 + L::OFF_C16 + 4u * (unsigned)(trow + z0);
     const float2 nxy = make_float2(-pi.x, -pi.y);
     const float nz = -pi.z;
     unsigned lofs = lbase, c16 = 0;
@@ -216,10 +219,10 @@ __device__ __forceinline__ void pass_a6_neighbours(const DevParams *__restrict__
         if constexpr (STAGED) return lds_f4(c16 + 16u * (unsigned)j);
         else return __ldg(P + j);
     };
-    sweep6<T, 4>(
+    sweep6<T, 4, L::LISTK>(
         cell_start, ga, gagb, num_cells, key, lbase, lofs,
-        [&](int r) {
-            if constexpr (STAGED) c16 = lds_u32(tab + 4u * (unsigned)r);
+        [&](int dc, int k) {
+            if constexpr (STAGED) c16 = lds_u32(tab + 4u * (unsigned)(dc * tstride + k));
         },
         [&](int j, int e, unsigned &lo) {
             const float4 p0 = ld(j), p1 = ld(j + 1), p2 = ld(j + 2), p3 = ld(j + 3);
@@ -296,9 +299,9 @@ __global__ void __launch_bounds__(T, 768 / T) k_pass_a6(const __grid_constant__ 
     float dens = 0.0f, pvx = 0.0f, pvy = 0.0f, pvz = 0.0f;
     if (staged) {
         mbar_wait(smem0 + L::OFF_MBAR, 0);
-        if (valid) pass_a6_neighbours<T, true>(g, a, cell_start, key, smem0, pi, ci, dens, pvx, pvy, pvz);
+        if (valid) pass_a6_neighbours<L, T, true>(g, a, cell_start, key, smem0, 3, 0, pi, ci, dens, pvx, pvy, pvz);
     } else if (valid) {
-        pass_a6_neighbours<T, false>(g, a, cell_start, key, smem0, pi, ci, dens, pvx, pvy, pvz);
+        pass_a6_neighbours<L, T, false>(g, a, cell_start, key, smem0, 3, 0, pi, ci, dens, pvx, pvy, pvz);
     }
     if (live) pass_a_finish(p, a, i, pi, ci, dens, pvx, pvy, pvz);
 }
@@ -306,11 +309,10 @@ __global__ void __launch_bounds__(T, 768 / T) k_pass_a6(const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------
 // pass B: ionic cell model + pressure / viscosity force + SPH Laplacian of Vm + integration and walls
 // (reference cpp:575-593, 515-573, 598-651).  PB = (pos.xyz, Vm) and VN = m/dens are the neighbour records of phase 1.
-template <int T, int STEP, bool STAGED>
+template <class L, int T, int STEP, bool STAGED>
 __device__ __forceinline__ void pass_b6_neighbours(const DevParams *__restrict__ g, const Arrays &a, const int *__restrict__ cell_start, const int key,
-                                                   const unsigned smem0, const float4 pi, const float4 vi, const float Vm_i, const float pres_i,
-                                                   float &ax, float &ay, float &az, float &Lsum) {
-    using L = Lay6<T, true>;
+                                                   const unsigned smem0, const int tstride, const int trow, const float4 pi, const float4 vi,
+                                                   const float Vm_i, const float pres_i, float &ax, float &ay, float &az, float &Lsum) {
     constexpr unsigned LSTEP6 = 4u * T;
     const int z0 = g->zero;  // == 0, loaded from global: what is derived from it stays in registers (see list_put)
     const float4 *__restrict__ PB = pinned(a.PB, z0);
@@ -321,7 +323,7 @@ __device__ __forceinline__ void pass_b6_neighbours(const DevParams *__restrict__
     const float a1 = g->bs_a1, b1 = g->bs_b1, a2 = g->bs_a2, b2 = g->bs_b2;
     const int ga = g->ga, gagb = g->ga * g->gb, num_cells = g->num_cells;
     const unsigned lbase = smem0 + L::OFF_LIST + 4u * (unsigned)(threadIdx.x + z0);
-    const unsigned tab = smem0 + L::OFF_C16 + (unsigned)z0;
+    const unsigned tab = smem0 + L::OFF_C16 + 4u * (unsigned)(trow + z0);
     const float2 nxy = make_float2(-pi.x, -pi.y), nzv = make_float2(-pi.z, -Vm_i);
     float L0 = 0.0f, L1 = 0.0f;  // two Laplacian accumulators: even / odd candidates of a row (as generation 4)
     unsigned lofs = lbase, c16 = 0, c4 = 0;
@@ -347,12 +349,13 @@ __device__ __forceinline__ void pass_b6_neighbours(const DevParams *__restrict__
         if constexpr (STAGED) return lds_f32(c4 + 4u * (unsigned)j);
         else return __ldg(VN + j);
     };
-    sweep6<T, STEP>(
+    sweep6<T, STEP, L::LISTK>(
         cell_start, ga, gagb, num_cells, key, lbase, lofs,
-        [&](int r) {
+        [&](int dc, int k) {
             if constexpr (STAGED) {
-                c16 = lds_u32(tab + 4u * (unsigned)r);
-                c4 = lds_u32(tab + 36u + 4u * (unsigned)r);
+                const unsigned q = tab + 4u * (unsigned)(dc * tstride + k);
+                c16 = lds_u32(q);
+                c4 = lds_u32(q + (L::OFF_C4 - L::OFF_C16));
             }
         },
         [&](int j, int e, unsigned &lo) {
@@ -451,9 +454,9 @@ __global__ void __launch_bounds__(T, 640 / T) k_pass_b6(const __grid_constant__ 
     float ax = 0.0f, ay = 0.0f, az = 0.0f, Lsum = 0.0f;
     if (staged) {
         mbar_wait(smem0 + L::OFF_MBAR, 0);
-        if (valid) pass_b6_neighbours<T, STEP, true>(g, a, cell_start, key, smem0, pi, vi, Vm_i, si.x, ax, ay, az, Lsum);
+        if (valid) pass_b6_neighbours<L, T, STEP, true>(g, a, cell_start, key, smem0, 3, 0, pi, vi, Vm_i, si.x, ax, ay, az, Lsum);
     } else if (valid) {
-        pass_b6_neighbours<T, STEP, false>(g, a, cell_start, key, smem0, pi, vi, Vm_i, si.x, ax, ay, az, Lsum);
+        pass_b6_neighbours<L, T, STEP, false>(g, a, cell_start, key, smem0, 3, 0, pi, vi, Vm_i, si.x, ax, ay, az, Lsum);
     }
     if (live) pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, fixed, ax, ay, az, Lsum, inv_mass, next_keys, next_rank, cell_count);
 }

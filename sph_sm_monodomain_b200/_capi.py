@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsphsm_b200.so")
+LIB_PATH = os.environ.get("SPHSM_LIB_PATH", os.path.join(HERE, "libsphsm_b200.so"))  # (override: kernel-variant experiments)
 
 NUM_KERNEL_GROUPS = 8
 PARTICLE_STRIDE = 132

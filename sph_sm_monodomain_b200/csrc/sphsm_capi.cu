@@ -21,7 +21,6 @@
 #include "sphsm_pass4.cuh"
 #include "sphsm_pass4w.cuh"
 #include "sphsm_pass6.cuh"
-#include "sphsm_pass7.cuh"
 #include "sphsm_sm.cuh"
 #include "sphsm_sort.cuh"
 #include "sphsm_types.cuh"
@@ -68,9 +67,6 @@ struct sphsm_handle {
     bool split = false;                    // slab step: exchange 2 in flight on the side stream beside the interior planes
     Arrays cur{}, alt{};
     uint32_t *keys[2] = {nullptr, nullptr}, *vals[2] = {nullptr, nullptr};
-    TileList tiles{};                // generation 7: the multi-row tiles of the current cell table (k_build_tiles)
-    cudaEvent_t ev_scan = nullptr, ev_tiles = nullptr;
-    bool tiles_pending = false;      // the builder is queued on the side stream: the passes wait for ev_tiles
     uint32_t *skeys = nullptr;       // counting sort: the cell key of every slot, in slot order (k_cell_scatter)
     uint32_t *key_sorted = nullptr;  // what the neighbour passes read: skeys, or the radix sort's sorted key buffer
     uint32_t *ghist = nullptr, *tile_state = nullptr, *tile_counter = nullptr;
@@ -178,17 +174,15 @@ static int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 4;
 static int g_stage6 = getenv("SPHSM_STAGE6") ? atoi(getenv("SPHSM_STAGE6")) : 1;
 static int g_t6 = getenv("SPHSM_T6") ? atoi(getenv("SPHSM_T6")) : 128;
 static int g_b_step6 = getenv("SPHSM_B_STEP6") ? atoi(getenv("SPHSM_B_STEP6")) : 2;
-static int g_b7_minb = getenv("SPHSM_B7_BLOCKS") ? atoi(getenv("SPHSM_B7_BLOCKS")) : 7;  // resident blocks per SM the tile force pass is compiled for (6 | 7 | 8)
 static int g_warp_path = getenv("SPHSM_WARP_PATH") ? atoi(getenv("SPHSM_WARP_PATH")) : 1;  // 0: small dense sets take the thread-per-particle kernels too
 extern "C" int sphsm_tune(const char *name, int value) {
     if (!name) return SPHSM_ERR_INVALID;
     const std::string n(name);
-    if (n == "pass" && (value == 4 || value == 6 || value == 7)) g_pass_gen = value;
+    if (n == "pass" && (value == 4 || value == 6)) g_pass_gen = value;
     else if (n == "stage6" && (value == 0 || value == 1)) g_stage6 = value;
     else if (n == "t6" && (value == 64 || value == 128)) g_t6 = value;
     else if (n == "b_step6" && (value == 2 || value == 4)) g_b_step6 = value;
     else if (n == "warp_path" && (value == 0 || value == 1)) g_warp_path = value;
-    else if (n == "b7_blocks" && value >= 6 && value <= 8) g_b7_minb = value;
     else return SPHSM_ERR_INVALID;
     return SPHSM_OK;
 }
@@ -355,22 +349,6 @@ static int setup_grid_buffers(sphsm_handle *h) {
     CU(cudaMemset(h->cell_count, 0, ((size_t)h->dp.num_cells + 2 + SCAN_IPT) * sizeof(uint32_t)));
     h->counts_ready = false;
     CU(cudaMalloc(&h->tile_sums, ((size_t)(h->dp.num_cells + 2) / SCAN_TILE + 2) * sizeof(uint32_t)));
-    // generation 7: tile list sized for the worst case of the greedy cut (two consecutive tiles of a row group hold more than
-    // TILE_T targets together) plus a tile per row group and the limbo / oversize chunks
-    {
-        if (h->tiles.rec) { cudaFree(h->tiles.rec); cudaFree(h->tiles.count); cudaFree(h->tiles.tickets); }
-        h->tiles = TileList{};
-        const long long groups = (long long)h->dp.gcl * ((h->dp.gb - 2 + TILE_R - 1) / TILE_R);
-        const long long cap_t = 3ll * h->alloc_n / TILE_T + 2 * groups + 1024;
-        if (cap_t < (1ll << 24)) {  // (absurdly fine grids keep the gathered passes)
-            h->tiles.capacity = (int)cap_t;
-            CU(cudaMalloc(&h->tiles.rec, (size_t)cap_t * TILE_INTS * sizeof(int)));
-            CU(cudaMalloc(&h->tiles.count, sizeof(int)));
-            CU(cudaMalloc(&h->tiles.tickets, TILE_TICKETS * sizeof(int)));
-            CU(cudaMemset(h->tiles.count, 0, sizeof(int)));
-            CU(cudaMemset(h->tiles.tickets, 0, TILE_TICKETS * sizeof(int)));
-        }
-    }
     int bits = 1;
     while ((1ll << bits) < (long long)h->dp.num_cells + 1) bits++;
     h->sort_passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
@@ -427,8 +405,6 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     for (cudaEvent_t *e : {&h->ev_in_ready, &h->ev_in_free, &h->ev_out_ready, &h->ev_out_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_scan, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->ev_tiles, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_x1, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming));
     h->launch_stream = h->stream;
@@ -476,9 +452,6 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     free_arrays(h->alt, false);
     for (int k = 0; k < 2; k++) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
     cudaFree(h->skeys);
-    cudaFree(h->tiles.rec); cudaFree(h->tiles.count); cudaFree(h->tiles.tickets);
-    if (h->ev_scan) cudaEventDestroy(h->ev_scan);
-    if (h->ev_tiles) cudaEventDestroy(h->ev_tiles);
     cudaFree(h->cell_count); cudaFree(h->tile_sums); cudaFree(h->big_cells); cudaFree(h->big_count);
     cudaFree(h->ghist); cudaFree(h->tile_state); cudaFree(h->tile_counter); cudaFree(h->cell_start); cudaFree(h->slot_of);
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);

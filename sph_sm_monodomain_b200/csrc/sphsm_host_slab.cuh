@@ -449,22 +449,22 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 CU(cudaEventRecord(h->ev_fork, h->stream));
                 CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
                 h->launch_stream = h->side_stream;
-                rc = launch_pass_a(h, 0, 2 * cap, 0, 0, m->rng_bnd, LK_BND);
+                rc = launch_pass_a(h, 0, 2 * cap, 0, 0, m->rng_bnd);
                 if (!rc) rc = pack2(h);
                 h->launch_stream = h->stream;
                 if (rc) return rc;
                 CU(cudaEventRecord(h->ev_bnd, h->side_stream));
-                if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_int, LK_INT)) != 0) return rc;  // (queued before the NCCL calls: they take host time)
+                if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_int)) != 0) return rc;  // (queued before the NCCL calls: they take host time)
                 CU(cudaEventRecord(h->ev_int, h->stream));
                 // pass B is cut two planes deep: the planes at least two away from a face read no boundary-plane record at all, so
                 // they follow pass A's interior directly; the two outer planes of either side wait for exchange 2 on the side stream
-                if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_int2, LK_INT2)) != 0) return rc;
+                if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_int2)) != 0) return rc;
                 if (g_host_prof_early() && h->pev[4]) CU(cudaEventRecord(h->pev[4], h->side_stream));
                 rc = nccl_exchange2(h, h->side_stream);
                 if (g_host_prof_early() && h->pev[5]) CU(cudaEventRecord(h->pev[5], h->side_stream));
                 return rc;
             }
-            if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_all, LK_ALL)) != 0) return rc;
+            if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_all)) != 0) return rc;
             if ((rc = pack2(h)) != 0) return rc;
             if (h->gt) h->gt->end_group(KG_PASS_A);
             *coll = COLL_EXCH2;
@@ -477,7 +477,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 CU(cudaStreamWaitEvent(h->side_stream, h->ev_int, 0));
                 h->launch_stream = h->side_stream;
                 rc = unpack2(h);
-                if (!rc) rc = launch_pass_b(h, 0, 4 * cap, diag, 0, 0, false, m->rng_bnd2, LK_BND2);
+                if (!rc) rc = launch_pass_b(h, 0, 4 * cap, diag, 0, 0, false, m->rng_bnd2);
                 // their new positions decide what the neighbours get next step: pack it now and let exchange 1 travel while the
                 // main stream is still busy with the inner planes
                 if (!rc) rc = [&]() -> int {
@@ -491,7 +491,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 return SPHSM_OK;
             }
             if ((rc = unpack2(h)) != 0) return rc;
-            if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_all, LK_ALL)) != 0) return rc;
+            if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_all)) != 0) return rc;
             return SPHSM_OK;
         }
         case 6: {  // the two streams meet; bookkeeping

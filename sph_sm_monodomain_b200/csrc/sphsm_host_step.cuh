@@ -54,39 +54,6 @@ static bool use_counting_sort(const sphsm_handle *h) {
 }
 
 // one pass over the full key: count per cell -> scan (= the cell table) -> scatter -> canonical in-cell order
-// generation 7: cut the fresh cell table into multi-row tiles (sphsm_pass7.cuh).  Only the table is needed, so the builder
-// runs on the side stream beside the scatter, the in-cell ordering and the gather; the passes wait for ev_tiles.
-static bool warp_path(const sphsm_handle *h);
-static bool tiles_wanted(const sphsm_handle *h) { return g_pass_gen == 7 && h->tiles.rec != nullptr; }
-static int launch_tile_builder(sphsm_handle *h, bool on_side) {
-    const DevParams &d = h->dp;
-    const int groups = (d.gb - 2 + TILE_R - 1) / TILE_R;
-    const int warps = groups * d.gcl + 1;
-    const int limbo_end = d.slab_on ? 0 : h->n;
-    cudaStream_t keep = h->launch_stream;
-    if (on_side && !h->dry_run) {
-        CU(cudaEventRecord(h->ev_scan, h->launch_stream));
-        CU(cudaStreamWaitEvent(h->side_stream, h->ev_scan, 0));
-    }
-    if (on_side) h->launch_stream = h->side_stream;
-    int rc = [&]() -> int {
-        if (!h->dry_run) CU(cudaMemsetAsync(h->tiles.count, 0, sizeof(int), h->launch_stream));
-        LAUNCH(k_build_tiles, cdiv((long long)warps * 32, 128), 128, h->cell_start, d.ga, d.gb, d.gcl, limbo_end, h->tiles);
-        return SPHSM_OK;
-    }();
-    h->launch_stream = keep;
-    if (rc) return rc;
-    if (on_side) {
-        if (!h->dry_run) CU(cudaEventRecord(h->ev_tiles, h->side_stream));
-        h->tiles_pending = true;
-    }
-    return SPHSM_OK;
-}
-static int wait_tiles(sphsm_handle *h) {  // on the current launch stream, before a tile pass
-    if (h->tiles_pending && !h->dry_run) CU(cudaStreamWaitEvent(h->launch_stream, h->ev_tiles, 0));
-    return SPHSM_OK;
-}
-
 // n_dev != nullptr (slab step): the entry count is *n_dev + n_add in device memory and h->n is an upper bound for the grids
 static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt, const int *n_dev = nullptr, int n_add = 0, int n_grid = -1) {
     const int n = n_grid >= 0 ? n_grid : h->n, m = h->dp.num_cells + 1;  // cells + the limbo bucket
@@ -97,11 +64,6 @@ static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt, const int *n_dev 
     LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
     LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles, h->big_count);
     LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start);
-    h->tiles_pending = false;
-    if (tiles_wanted(h) && !warp_path(h)) {
-        int rc = launch_tile_builder(h, h->launch_stream == h->stream && !h->profiling);
-        if (rc) return rc;
-    }
     LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0], h->skeys, n_dev, n_add);
     h->key_sorted = h->skeys;
     LAUNCH(k_cell_sort_ids, cdiv(h->dp.num_cells, 256), 256, h->cell_start, h->vals[0], h->cur.ID, h->dp.num_cells, h->big_cells, h->big_count);
@@ -147,14 +109,7 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt, const int *n_dev = nullptr
 // n_dev != nullptr: the live count is read from device memory (grid sized for h->n, an upper bound)
 static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool bounds_done = false, const int *n_dev = nullptr, int n_grid = -1) {
     const int n = n_grid >= 0 ? n_grid : h->n, src = h->sorted_buf;
-    if (!bounds_done && !h->bounds_ready) {
-        LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
-        h->tiles_pending = false;
-        if (tiles_wanted(h) && !warp_path(h)) {
-            int rc = launch_tile_builder(h, false);
-            if (rc) return rc;
-        }
-    }
+    if (!bounds_done && !h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
     if (fuse_goal) {
         if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev);
         else LAUNCH(k_reorder_goal<false>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev);
@@ -377,60 +332,15 @@ static int prepare6(sphsm_handle *h, K kern, unsigned bytes) {  // dynamic share
         }                                                                                                               \
     } while (0)
 
-// generation 7 launches are defined by PLANES, not slots: which = LK_ALL (every owned plane; on one GPU everything, the limbo
-// tiles of plane -1 included) | LK_INT / LK_BND (planes at least one away from both faces / the first and last owned plane)
-// | LK_INT2 / LK_BND2 (the same, two planes deep).  Window coordinates: plane 0 and plane gcl - 1 are the halo planes of a slab.
-enum { LK_ALL = 0, LK_INT, LK_BND, LK_INT2, LK_BND2 };
-static PlaneSet plane_set(const sphsm_handle *h, int which) {
-    const int gcl = h->dp.gcl;
-    if (!h->dp.slab_on) return PlaneSet{-1, gcl, 0, 0};
-    switch (which) {
-        case LK_INT: return PlaneSet{2, gcl - 2, 0, 0};
-        case LK_BND: return gcl - 2 > 2 ? PlaneSet{1, gcl - 1, 2, gcl - 2} : PlaneSet{1, gcl - 1, 0, 0};
-        case LK_INT2: return PlaneSet{3, gcl - 3, 0, 0};
-        case LK_BND2: return gcl - 3 > 3 ? PlaneSet{1, gcl - 1, 3, gcl - 3} : PlaneSet{1, gcl - 1, 0, 0};
-        default: return PlaneSet{1, gcl - 1, 0, 0};
-    }
-}
-static int tile_grid(const sphsm_handle *h, int blocks_per_sm) {
-    static int sms = 0;
-    if (!sms) {
-        cudaDeviceProp prop;
-        sms = cudaGetDeviceProperties(&prop, h->prm.device) == cudaSuccess ? prop.multiProcessorCount : 148;
-    }
-    return sms * blocks_per_sm;
-}
-#define LAUNCH7(kern, WITH4, grid, ...)                                                                                 \
-    do {                                                                                                                \
-        const unsigned bytes_ = Lay7<WITH4>::BYTES;                                                                     \
-        int rc_ = prepare6(h, kern, bytes_);                                                                            \
-        if (rc_) return rc_;                                                                                            \
-        if (!h->dry_run) kern<<<(grid), TILE_T, bytes_, h->launch_stream>>>(__VA_ARGS__);                                \
-        h->launches++;                                                                                                  \
-        if (g_sync_debug) {                                                                                             \
-            cudaError_t e_ = cudaStreamSynchronize(h->launch_stream);                                                   \
-            if (e_ != cudaSuccess) {                                                                                    \
-                h->err = std::string("kernel ") + #kern + " failed: " + cudaGetErrorString(e_);                         \
-                fprintf(stderr, "[sphsm] %s\n", h->err.c_str());                                                        \
-                return SPHSM_ERR_CUDA;                                                                                  \
-            }                                                                                                           \
-        }                                                                                                               \
-    } while (0)
-
 // slots [begin, end) minus the hole [hole_b, hole_e).  rng != nullptr (slab step): the range is read from device memory
 // ({begin, end, hole_begin, hole_len}) and [begin, end) / the hole only size the grid: `end - begin - hole` is an upper bound of the
 // target count, and with a hole the two sides may hold up to that many targets EACH (generation 6 cuts them into blocks separately).
-static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0, const int *rng = nullptr, int which = LK_ALL) {
+static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, int hole_e = 0, const int *rng = nullptr) {
     const int count = end - begin - (hole_e - hole_b);
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
-    if (tiles_wanted(h) && !warp_path(h)) {
-        int rc = wait_tiles(h);
-        if (rc) return rc;
-        LAUNCH7(k_pass_a7, false, tile_grid(h, 8), d, h->d_dp, h->cur, h->cell_start, h->key_sorted, h->tiles, which, plane_set(h, which), g_stage6);
-        return SPHSM_OK;
-    }
+
     const int g6_128 = rng ? cdiv(count, 128) + 2 : grid6(begin, end, hole_b, hole_e, 128), g6_64 = rng ? cdiv(count, 64) + 2 : grid6(begin, end, hole_b, hole_e, 64);
     if (warp_path(h)) LAUNCH(k_pass_a4w, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->cell_start, count, rng);
     else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, rng);
@@ -444,33 +354,14 @@ static int launch_pass_b6(sphsm_handle *h, const DevParams &d, int grid, bool di
     else LAUNCH6((k_pass_b6<T, STEP, false>), T, true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, g_stage6, rng);
     return SPHSM_OK;
 }
-template <int STEP>
-static int launch_pass_b7(sphsm_handle *h, const DevParams &d, bool diag, uint32_t *nk, uint32_t *nr, uint32_t *ncnt, int which) {
-    const int grid = tile_grid(h, g_b7_minb);
-    if (g_b7_minb == 8) {
-        if (diag) LAUNCH7((k_pass_b7<STEP, true, 8>), true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, h->tiles, 8 + which, plane_set(h, which), g_stage6);
-        else LAUNCH7((k_pass_b7<STEP, false, 8>), true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, h->tiles, 8 + which, plane_set(h, which), g_stage6);
-    } else if (g_b7_minb == 6) {
-        if (diag) LAUNCH7((k_pass_b7<STEP, true, 6>), true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, h->tiles, 8 + which, plane_set(h, which), g_stage6);
-        else LAUNCH7((k_pass_b7<STEP, false, 6>), true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, h->tiles, 8 + which, plane_set(h, which), g_stage6);
-    } else {
-        if (diag) LAUNCH7((k_pass_b7<STEP, true, 7>), true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, h->tiles, 8 + which, plane_set(h, which), g_stage6);
-        else LAUNCH7((k_pass_b7<STEP, false, 7>), true, grid, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, h->tiles, 8 + which, plane_set(h, which), g_stage6);
-    }
-    return SPHSM_OK;
-}
 static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hole_b = 0, int hole_e = 0, bool file_counts = false,
-                         const int *rng = nullptr, int which = LK_ALL) {
+                         const int *rng = nullptr) {
     uint32_t *nk = file_counts ? h->keys[0] : nullptr, *nr = file_counts ? h->keys[1] : nullptr, *ncnt = file_counts ? h->cell_count : nullptr;
     const int count = end - begin - (hole_e - hole_b);
     if (count <= 0) return SPHSM_OK;
     DevParams d = h->dp;
     d.own_begin = begin; d.own_end = end; d.hole_begin = hole_b; d.hole_len = hole_e - hole_b;
-    if (tiles_wanted(h) && !warp_path(h)) {
-        int rc = wait_tiles(h);
-        if (rc) return rc;
-        return g_b_step6 == 4 ? launch_pass_b7<4>(h, d, diag, nk, nr, ncnt, which) : launch_pass_b7<2>(h, d, diag, nk, nr, ncnt, which);
-    }
+
     if (warp_path(h)) {
         if (diag) LAUNCH(k_pass_b4w<true>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count, rng);
         else LAUNCH(k_pass_b4w<false>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count, rng);
@@ -592,9 +483,9 @@ static std::string step_signature(const sphsm_handle *h) {
     put(&h->dp, sizeof(DevParams));
     put(&h->prm, sizeof(sphsm_params));
     const void *ptrs[] = {h->cell_start, h->cell_count, h->tile_sums, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->big_cells, h->big_count,
-                          h->sm, h->partial, h->totals, h->d_dp, h->ghist, h->tile_state, h->tile_counter, h->scratch, h->skeys, h->tiles.rec};
+                          h->sm, h->partial, h->totals, h->d_dp, h->ghist, h->tile_state, h->tile_counter, h->scratch, h->skeys};
     put(ptrs, sizeof(ptrs));
-    const int flags[] = {h->counts_ready, h->bounds_ready, h->sorted_buf, g_pass_gen, h->red_blocks, h->sort_passes, (int)h->grid_valid, (int)warp_path(h), g_stage6, g_t6, g_b_step6, g_b7_minb};
+    const int flags[] = {h->counts_ready, h->bounds_ready, h->sorted_buf, g_pass_gen, h->red_blocks, h->sort_passes, (int)h->grid_valid, (int)warp_path(h), g_stage6, g_t6, g_b_step6};
     put(flags, sizeof(flags));
     return sig;
 }

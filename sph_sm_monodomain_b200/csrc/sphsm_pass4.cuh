@@ -21,7 +21,10 @@
 
 namespace sphsm {
 
-constexpr int LIST_K = 16;  // in-range list entries per lane between drains
+#ifndef SPHSM_LIST_K
+#define SPHSM_LIST_K 16
+#endif
+constexpr int LIST_K = SPHSM_LIST_K;  // in-range list entries per lane between drains
 
 __device__ __forceinline__ float rsqrt_ftz(float x) {
     float y;
@@ -165,11 +168,9 @@ __device__ __forceinline__ void pass_a_finish(const DevParams &p, const Arrays &
 
 // ---------------------------------------------------------------------------------------------------
 // pass A: density / pressure + XSPH intermediate velocity (reference cpp:448-513, 669-701)
-__global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
-                                                const int *__restrict__ cell_start, const uint32_t *__restrict__ skey, const int *__restrict__ rng) {
-    __shared__ int s_list[LIST_K * PT4];
-    const int i = launch_slot(launch_range(p, rng), blockIdx.x * PT4 + threadIdx.x);
-    if (i < 0) return;
+// one target of pass A: slot i, in-range list of this lane at shared-memory address slist (stride LSTEP)
+__device__ __forceinline__ void pass_a4_one(const DevParams &p, const DevParams *__restrict__ g, const Arrays &a, const int *__restrict__ cell_start,
+                                            const uint32_t *__restrict__ skey, const int i, const unsigned slist) {
     const float4 pi = a.P[i];
     const float4 ci = a.C[i];
     const int z0 = g->zero;  // == 0, loaded from global: what is derived from it stays in registers (see list_put)
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_consta
     const float4 *__restrict__ C = a.C;
     const float h2 = g->h2, c6 = g->c_poly6;
     const int ga = g->ga, gagb = g->ga * g->gb;
-    const unsigned lbase = (unsigned)__cvta_generic_to_shared(s_list) + 4u * (unsigned)(threadIdx.x + z0);
+    const unsigned lbase = slist + 4u * (unsigned)z0;
     const float2 nxy = make_float2(-pi.x, -pi.y);
     const float nz = -pi.z;
     float dens = 0.0f, pvx = 0.0f, pvy = 0.0f, pvz = 0.0f;
@@ -232,6 +233,13 @@ __global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_consta
             });
     }
     pass_a_finish(p, a, i, pi, ci, dens, pvx, pvy, pvz);
+}
+__global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+                                                const int *__restrict__ cell_start, const uint32_t *__restrict__ skey, const int *__restrict__ rng) {
+    __shared__ int s_list[LIST_K * PT4];
+    const int i = launch_slot(launch_range(p, rng), blockIdx.x * PT4 + threadIdx.x);
+    if (i < 0) return;
+    pass_a4_one(p, g, a, cell_start, skey, i, (unsigned)__cvta_generic_to_shared(s_list) + 4u * threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -313,13 +321,9 @@ __device__ __forceinline__ void pass_b_finish(const DevParams &p, const Arrays &
 // cell_count != nullptr: the thread also files its particle's NEW position for the next step's counting sort (key, provisional
 // rank in the cell, per-cell count — what k_cell_count does, without re-reading the positions)
 template <bool DIAG>
-__global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
-                                                float4 *__restrict__ Pout, const int *__restrict__ cell_start, const uint32_t *__restrict__ skey,
-                                                uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count,
-                                                const int *__restrict__ rng) {
-    __shared__ int s_list[LIST_K * PT4];
-    const int i = launch_slot(launch_range(p, rng), blockIdx.x * PT4 + threadIdx.x);
-    if (i < 0) return;
+__device__ __forceinline__ void pass_b4_one(const DevParams &p, const DevParams *__restrict__ g, const Arrays &a, float4 *__restrict__ Pout,
+                                            const int *__restrict__ cell_start, const uint32_t *__restrict__ skey, uint32_t *__restrict__ next_keys,
+                                            uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count, const int i, const unsigned slist) {
     const float4 pi = a.P[i];
     const float4 vi = a.V[i];
     float4 e4 = a.E[i];
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
     const float sp2 = g->r2_spiky;
     const float a1 = g->bs_a1, b1 = g->bs_b1, a2 = g->bs_a2, b2 = g->bs_b2;
     const int ga = g->ga, gagb = g->ga * g->gb;
-    const unsigned lbase = (unsigned)__cvta_generic_to_shared(s_list) + 4u * (unsigned)(threadIdx.x + z0);
+    const unsigned lbase = slist + 4u * (unsigned)z0;
     const float2 nxy = make_float2(-pi.x, -pi.y), nzv = make_float2(-pi.z, -Vm_i);
     float ax = 0.0f, ay = 0.0f, az = 0.0f, L = 0.0f, L1 = 0.0f;  // two Laplacian accumulators: the pair's terms are independent
     unsigned lofs = lbase;
@@ -417,6 +421,16 @@ __global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_consta
             });
     }
     pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, fixed, ax, ay, az, L + L1, inv_mass, next_keys, next_rank, cell_count);
+}
+template <bool DIAG>
+__global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+                                                float4 *__restrict__ Pout, const int *__restrict__ cell_start, const uint32_t *__restrict__ skey,
+                                                uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count,
+                                                const int *__restrict__ rng) {
+    __shared__ int s_list[LIST_K * PT4];
+    const int i = launch_slot(launch_range(p, rng), blockIdx.x * PT4 + threadIdx.x);
+    if (i < 0) return;
+    pass_b4_one<DIAG>(p, g, a, Pout, cell_start, skey, next_keys, next_rank, cell_count, i, (unsigned)__cvta_generic_to_shared(s_list) + 4u * threadIdx.x);
 }
 
 }  // namespace sphsm

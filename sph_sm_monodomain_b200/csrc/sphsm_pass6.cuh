@@ -1,5 +1,13 @@
-// sphsm_pass6.cuh — the production neighbour passes, sixth generation: the stencil rows of a whole block of targets are staged in
-// shared memory with 1-D bulk copies (cp.async.bulk + mbarrier, the TMA engine), and phase 1 reads shared memory.
+// sphsm_pass6.cuh — the neighbour passes with the stencil rows of a whole block of targets staged in shared memory by 1-D bulk
+// copies (cp.async.bulk + mbarrier, the TMA engine); phase 1 reads shared memory.  Selected with SPHSM_PASS=6 /
+// sphsm_tune("pass", 6); NOT the default: measured at 8M on one B200 it is slower than the gathered passes of sphsm_pass4.cuh
+// (pass A 548 us against 469, pass B 859 against 716; ncu profiles/r02_gen6_pass_{a,b}.json, SASS excerpt
+// profiles/r02_gen6_sass_excerpt.txt).  The staging itself does what it was built for — the candidate-pair loops drop to 18 % of the
+// warp samples while issuing 48 % of the instructions — but nine spans of ~T records are 280 B of shared memory per target: 5 blocks
+// = 20 warps per SM (gathered: 32), and with so few warps the block start-up chain (keys -> cell table -> copies), phase 2's L2
+// gathers and the epilogue's atomics are exposed (12 % of the samples wait at the block barrier alone).  Sharing the spans between
+// four adjacent cell rows (multi-row tiles, 100 B per target) was built as well and lost to register pressure (two sweeps plus
+// the tile bookkeeping need 80-96 registers; 64-72 spill: 1124-1579 us) — DESIGN.md section 4.
 //
 // What generation 4 left on the table (ncu profiles/r01_v8_pass_{a,b}.json and their source pages): both passes are issue / L1
 // bound with HALF of the pair loop's stall samples on one instruction, the first use of the gathered candidate records

@@ -29,11 +29,6 @@ VARIANTS = {
     "gen6_t64_s2": dict(**{"pass": 6}, stage6=1, t6=64, b_step6=2),
     "gen6_t64_s4": dict(**{"pass": 6}, stage6=1, t6=64, b_step6=4),
     "gen6_unstaged": dict(**{"pass": 6}, stage6=0, t6=128, b_step6=2),
-    "gen7_b7_s2": dict(**{"pass": 7}, stage6=1, b_step6=2, b7_blocks=7),
-    "gen7_b8_s2": dict(**{"pass": 7}, stage6=1, b_step6=2, b7_blocks=8),
-    "gen7_b6_s2": dict(**{"pass": 7}, stage6=1, b_step6=2, b7_blocks=6),
-    "gen7_b7_s4": dict(**{"pass": 7}, stage6=1, b_step6=4, b7_blocks=7),
-    "gen7_unstaged": dict(**{"pass": 7}, stage6=0, b_step6=2, b7_blocks=7),
 }
 
 

@@ -356,7 +356,19 @@ static int setup_grid_buffers(sphsm_handle *h) {
     return SPHSM_OK;
 }
 
+static int create_impl(const sphsm_params *p, sphsm_handle **out, sphsm_handle **partial);
 extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
+    // a failure after the handle exists (a CUDA call, an allocation) must not leak its streams, events and device arrays
+    sphsm_handle *partial = nullptr;
+    const int rc = create_impl(p, out, &partial);
+    if (rc != SPHSM_OK && partial) {
+        const std::string why = partial->err.empty() ? g_create_error : partial->err;
+        sphsm_destroy(partial);
+        g_create_error = why;  // sphsm_last_error(NULL) reports it
+    }
+    return rc;
+}
+static int create_impl(const sphsm_params *p, sphsm_handle **out, sphsm_handle **partial) {
     sphsm_handle *h = nullptr;
     if (!p || !out) return fail(nullptr, SPHSM_ERR_INVALID, "null argument");
     if (p->struct_size != sizeof(sphsm_params)) return fail(nullptr, SPHSM_ERR_INVALID, "sphsm_params.struct_size mismatch (ABI)");
@@ -378,6 +390,7 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
         }
     }
     h = nh;
+    *partial = nh;
     // slab mode appends up to two halo messages behind the local particles before every sort: room for them
     if (p->slab_axis >= 0) {
         int hc = p->reserved[0];  // halo capacity override (particles per message)
@@ -441,6 +454,7 @@ extern "C" int sphsm_create(const sphsm_params *p, sphsm_handle **out) {
     CU(cudaEventCreate(&h->ev_tm[0]));
     CU(cudaEventCreate(&h->ev_tm[1]));
     *out = h;
+    *partial = nullptr;
     return SPHSM_OK;
 }
 

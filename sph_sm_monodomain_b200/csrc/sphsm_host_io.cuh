@@ -57,8 +57,15 @@ extern "C" int sphsm_load_state(sphsm_handle *h, const char *path) {
     if (rc) return rc;
     sp.device = h->prm.device; sp.capacity = h->prm.capacity; sp.slab_axis = h->prm.slab_axis; sp.strict = h->prm.strict;
     sp.diagnostics = h->prm.diagnostics;
+    memcpy(sp.reserved, h->prm.reserved, sizeof sp.reserved);  // the handle's own switches (sort algorithm, graphs ...) are not state
+    const sphsm_params before = h->prm;
     if ((rc = sphsm_set_params(h, &sp)) != 0) return rc;
-    if ((rc = sphsm_upload_aos(h, buf.data(), hd.n, SPHSM_PARTICLE_STRIDE)) != 0) return rc;
+    if ((rc = sphsm_upload_aos(h, buf.data(), hd.n, SPHSM_PARTICLE_STRIDE)) != 0) {
+        const std::string why = h->err;
+        sphsm_set_params(h, &before);  // a failed load leaves the handle as it was
+        h->err = why;
+        return rc;
+    }
     h->total_steps = hd.total_steps;
     return SPHSM_OK;
 }

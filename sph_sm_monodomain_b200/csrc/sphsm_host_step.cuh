@@ -343,7 +343,8 @@ static int launch_pass_a(sphsm_handle *h, int begin, int end, int hole_b = 0, in
 
     const int g6_128 = rng ? cdiv(count, 128) + 2 : grid6(begin, end, hole_b, hole_e, 128), g6_64 = rng ? cdiv(count, 64) + 2 : grid6(begin, end, hole_b, hole_e, 64);
     if (warp_path(h)) LAUNCH(k_pass_a4w, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->cell_start, count, rng);
-    else if (g_pass_gen == 4) LAUNCH(k_pass_a4, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, rng);
+    else if (g_pass_gen == 4 && rng) LAUNCH(k_pass_a4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, rng);
+    else if (g_pass_gen == 4) LAUNCH(k_pass_a4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, rng);
     else if (g_t6 == 64) LAUNCH6(k_pass_a6<64>, 64, false, g6_64, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6, rng);
     else LAUNCH6(k_pass_a6<128>, 128, false, g6_128, d, h->d_dp, h->cur, h->cell_start, h->key_sorted, g_stage6, rng);
     return SPHSM_OK;
@@ -366,8 +367,10 @@ static int launch_pass_b(sphsm_handle *h, int begin, int end, bool diag, int hol
         if (diag) LAUNCH(k_pass_b4w<true>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count, rng);
         else LAUNCH(k_pass_b4w<false>, cdiv((long long)count * 32, PTW), PTW, d, h->cur, h->alt.P, h->cell_start, nk, nr, ncnt, count, rng);
     } else if (g_pass_gen == 4) {
-        if (diag) LAUNCH(k_pass_b4<true>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, rng);
-        else LAUNCH(k_pass_b4<false>, cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, rng);
+        if (diag && rng) LAUNCH((k_pass_b4<true, true>), cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, rng);
+        else if (diag) LAUNCH((k_pass_b4<true, false>), cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, rng);
+        else if (rng) LAUNCH((k_pass_b4<false, true>), cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, rng);
+        else LAUNCH((k_pass_b4<false, false>), cdiv(count, PT4), PT4, d, h->d_dp, h->cur, h->alt.P, h->cell_start, h->key_sorted, nk, nr, ncnt, rng);
     } else if (g_t6 == 64) {
         const int grid = rng ? cdiv(count, 64) + 2 : grid6(begin, end, hole_b, hole_e, 64);
         return g_b_step6 == 4 ? launch_pass_b6<64, 4>(h, d, grid, diag, nk, nr, ncnt, rng) : launch_pass_b6<64, 2>(h, d, grid, diag, nk, nr, ncnt, rng);

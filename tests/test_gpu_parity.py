@@ -16,7 +16,9 @@ Tolerances (BASELINE.json north_star: neighbour sets bit-exact; density, force, 
 * 1000-step trajectories (fast path) ......... the dynamics amplify rounding differences (stiff pressure, rho ~ 30x
   rest density): the reference's OWN two builds (-Ofast as shipped vs -O2) drift apart by up to 5e-2 (max) / 5e-4
   (mean) on cfg1 — tests/golden/ref_spread.json, tools/make_ref_spread.py.  Bound: max |dpos| <= max(5e-3, 3x that
-  spread), mean |dpos| <= max(2e-4, 3x), Vm likewise (5x); strict mode is bit-exact over the same runs.
+  spread), mean |dpos| <= max(2e-4, 3x), Vm likewise (5x) — and never more than 3x what round 2 achieved at that checkpoint
+  (tests/golden/trajectory_achieved_r02.json: 2.6e-6 after one step, 1.1e-2 / 1.1e-3 after 100 steps of cfg1 / cfg2, 4e-2 / 9e-2
+  after 1000); strict mode is bit-exact over the same runs.
 """
 import json
 import os
@@ -177,8 +179,11 @@ def test_fused_step_vs_golden(Sim, name, parity_record):
 
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_fused_step_vs_double_moment_oracle(Sim, name, parity_record):
-    """One whole fused step against the oracle with double moment accumulation (the oracle of record for the
-    summation order at large N, SURVEY.md §7 hard part 3): same tolerance classes as against the float reference."""
+    """One whole fused step of the PRODUCTION kernels against the oracle with double moment accumulation (the oracle of record
+    for the summation order, SURVEY.md §7 hard part 3): every field within 1e-5 (2e-5 with the quadratic mode's truncated
+    Jacobi inverse, Q7) — positions, goal, density, pressure, voltage AND the velocity-like fields — except acc, a cancelling sum
+    whose viscosity part multiplies the (within-tolerance) velocity differences between neighbours by V mu Visco(r) / rho: 5e-4 of
+    its infinity norm (achieved: <= 1.8e-4, profiles/parity_r02.json)."""
     g, kw = load_golden(name)
     quadratic = CONFIGS[name]["quadratic"]
     params = make_params(g)
@@ -191,8 +196,9 @@ def test_fused_step_vs_double_moment_oracle(Sim, name, parity_record):
     worst = {}
     for st in range(2, 8):
         for f in STAGE_OUT[st]:
-            worst[f] = assert_close(f, got[f], want[f], params, tol=whole_step_tol(f, quadratic))
-            parity_record("fused_step_vs_double_moment_oracle", name, f, worst[f], whole_step_tol(f, quadratic))
+            tol = 5e-4 if f == "acc" else (2 * TOL if quadratic else TOL)
+            worst[f] = assert_close(f, got[f], want[f], params, tol=tol)
+            parity_record("fused_step_vs_double_moment_oracle", name, f, worst[f], tol)
     print(name, "fused step 1 vs double-moment oracle", {k: f"{v:.2e}" for k, v in worst.items()})
 
 
@@ -232,6 +238,10 @@ def test_trajectory_deviation_bounded(Sim, name, parity_record):
     sim, g = gpu_from_golden(Sim, name, diagnostics=False)
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_spread.json")) as fh:
         spread = json.load(fh)["spread"][name]
+    # what round 2 actually achieved (deterministic kernels: the same numbers every run): every bound below is the smaller of the
+    # spread-based one and three times that
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trajectory_achieved_r02.json")) as fh:
+        achieved = json.load(fh)["achieved"]
     done = 0
     for cp in [int(c) for c in g["checkpoints"]]:
         done = advance_to(sim, g, done, cp)
@@ -242,12 +252,17 @@ def test_trajectory_deviation_bounded(Sim, name, parity_record):
         vm_scale = max(1.0, float(np.abs(g[f"step{cp}.Vm"]).max()))
         print(f"{name} step {cp}: |dpos| max {dpos.max():.3e} mean {dpos.mean():.3e} (reference's own spread "
               f"{ref['pos_max']:.3e} / {ref['pos_mean']:.3e}); |dVm| max {dvm.max():.3e} (own spread {ref['vm_max']:.3e})")
-        parity_record("trajectory_deviation", f"{name}/step{cp}", "pos_max", dpos.max(), max(5e-3, 3 * ref["pos_max"]))
-        parity_record("trajectory_deviation", f"{name}/step{cp}", "pos_mean", dpos.mean(), max(2e-4, 3 * ref["pos_mean"]))
-        parity_record("trajectory_deviation", f"{name}/step{cp}", "vm_max", dvm.max(), max(1e-3 * vm_scale, 5 * ref["vm_max"]))
-        assert dpos.max() <= max(5e-3, 3 * ref["pos_max"]), (cp, dpos.max())
-        assert dpos.mean() <= max(2e-4, 3 * ref["pos_mean"]), (cp, dpos.mean())
-        assert dvm.max() <= max(1e-3 * vm_scale, 5 * ref["vm_max"]), (cp, dvm.max())
+        got_r2 = achieved.get(f"{name}/step{cp}", {})
+        tight = lambda key, floor, old: min(old, max(3 * got_r2[key], floor)) if key in got_r2 else old  # noqa: E731
+        b_pos_max = tight("pos_max", 1e-6, max(5e-3, 3 * ref["pos_max"]))
+        b_pos_mean = tight("pos_mean", 1e-7, max(2e-4, 3 * ref["pos_mean"]))
+        b_vm_max = tight("vm_max", 1e-6 * vm_scale, max(1e-3 * vm_scale, 5 * ref["vm_max"]))
+        parity_record("trajectory_deviation", f"{name}/step{cp}", "pos_max", dpos.max(), b_pos_max)
+        parity_record("trajectory_deviation", f"{name}/step{cp}", "pos_mean", dpos.mean(), b_pos_mean)
+        parity_record("trajectory_deviation", f"{name}/step{cp}", "vm_max", dvm.max(), b_vm_max)
+        assert dpos.max() <= b_pos_max, (cp, dpos.max(), b_pos_max)
+        assert dpos.mean() <= b_pos_mean, (cp, dpos.mean(), b_pos_mean)
+        assert dvm.max() <= b_vm_max, (cp, dvm.max(), b_vm_max)
         assert dvm.mean() <= max(1e-4 * vm_scale, 5 * ref["vm_mean"]), (cp, dvm.mean())
         assert np.array_equal(got["stim"], g[f"step{cp}.stim"])
 

@@ -206,6 +206,22 @@ def stim_box_of(pos, dims):
     return (-1.0, -1.0, -1.0), (x0 + 8 * s - 0.5 * s, 1e9, 1e9)
 
 
+def pacing_schedule(start, nsteps, period, off_after):
+    """The pacing protocol of BASELINE configs[4] as a list of actions covering steps [start, start + nsteps): ("stim",) before every
+    step k with k % period == 0, ("off",) before every step with k % period == off_after, ("run", m) for m uninterrupted steps."""
+    out, k, end = [], start, start + nsteps
+    while k < end:
+        ph = k % period
+        if ph == 0:
+            out.append(("stim",))
+        if ph == off_after:
+            out.append(("off",))
+        nxt = min(end, k - ph + (off_after if ph < off_after else period))
+        out.append(("run", nxt - k))
+        k = nxt
+    return out
+
+
 def make_sim(pos, world, fixed, stim, quadratic, device, world_size, rank, dist, torch, parts=None, axis=None, **kw):
     """A handle with the workload loaded; with world_size > 1 also its NCCL communicator (id broadcast from rank 0) and slab."""
     from sph_sm_monodomain_b200 import Sim
@@ -372,17 +388,13 @@ def run_ours(args, wl, rank, world_size, local_rank):
         if not pacing:
             sim.Animation(nsteps)
             return
-        period, off_after = pacing
-        k, end = start, start + nsteps
-        while k < end:
-            ph = k % period
-            if ph == 0:
+        for act in pacing_schedule(start, nsteps, *pacing):
+            if act[0] == "stim":
                 sim.set_stim_box(box_lo, box_hi, 300.0)
-            if ph == off_after:
+            elif act[0] == "off":
                 sim.turnOffStim()
-            nxt = min(end, k - ph + (off_after if ph < off_after else period))
-            sim.Animation(nxt - k)
-            k = nxt
+            else:
+                sim.Animation(act[1])
 
     # ---- device-resident throughput -----------------------------------------------------------------------------
     # clocks / throttle reasons are sampled from before the warm-up until after the timed region (a strong-scaled timed

@@ -139,6 +139,11 @@ struct sphsm_handle {
     int n_bound = 0;                       // upper bound of the live slot count the grids of the slab step are sized for
     int own_bound = 0;                     // likewise for the owned slots
     int *d_count = nullptr;                // sphsm_download_owned_async: the owned count of the queued gather
+    // SPHSM_TRACE=<step>: CUDA events at the phase boundaries of three consecutive slab steps starting at <step>, on both streams, read
+    // only after the third one (nothing synchronises inside the traced steps); printed by rank 0 and the last rank (trace_mark / trace_dump)
+    struct TraceEv { cudaEvent_t ev; const char *label; int stream; };
+    std::vector<TraceEv> trace;
+    int trace_from = -1;
     // exchange 1 of the NEXT step issued at the end of a step, behind pass B on the outer planes (it travels while the interior
     // planes are still being integrated).  Anything that changes particle state other than stimulation values between two steps
     // voids it (x1_early_valid = false): the next step then classifies and exchanges again, on every rank alike — state mutators
@@ -680,11 +685,15 @@ __global__ void k_fix_rule(const __grid_constant__ DevParams p, int n, Arrays a,
     }
 }
 
+// n_dev != nullptr (slab mode, where the host's count may lag the device): only the live slots [0, *n_dev) are touched — slots behind
+// them hold stale copies of particles that live elsewhere in the array, and freezing one of those would overwrite the frozen
+// values of the real one
 __global__ void k_set_masks(const __grid_constant__ DevParams p, int n, Arrays a, const uint8_t *__restrict__ fixed, const float *__restrict__ stim,
-                            FreezeSrc fz) {
+                            FreezeSrc fz, const int *__restrict__ n_dev) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= (n_dev ? min(*n_dev, n) : n)) return;
     const int id = a.ID[s];
+    if (id < 0) return;
     if (fixed) {
         const int was = __float_as_int(a.O[s].w);
         if (fixed[id] && !was) {
@@ -964,7 +973,7 @@ extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const floa
     if (fixed) CU(cudaMemcpyAsync(h->d_itmp, fixed, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     if (h->n > 0)
         LAUNCH(k_set_masks, cdiv(h->n, 256), 256, h->dp, h->n, h->cur, fixed ? (const uint8_t *)h->d_itmp : nullptr, stim ? h->d_tmp : nullptr,
-               freeze_source(h));
+               freeze_source(h), (const int *)nullptr);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
     if (fixed) h->rest_dirty = true;

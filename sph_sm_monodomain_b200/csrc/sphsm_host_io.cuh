@@ -115,7 +115,7 @@ extern "C" int sphsm_set_masks_async(sphsm_handle *h, const uint8_t *fixed, cons
     const int n_k = h->dp.slab_on ? std::max(h->n_bound, h->n) : h->n;
     if (n_k > 0)
         LAUNCH(k_set_masks, cdiv(n_k, 256), 256, h->dp, n_k, h->cur, fixed ? (const uint8_t *)h->io_in_b : nullptr, stim ? h->io_in_f : nullptr,
-               freeze_source(h));
+               freeze_source(h), h->dp.slab_on ? (const int *)&h->d_meta[h->meta_cur]->n_live : (const int *)nullptr);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ev_in_free, h->stream));
     if (fixed) h->rest_dirty = true;

@@ -302,6 +302,37 @@ static int unpack2(sphsm_handle *h) {
     return SPHSM_OK;
 }
 
+// ---- SPHSM_TRACE: event timeline of the slab step ------------------------------------------------------------------------
+static bool trace_on(sphsm_handle *h) {
+    if (h->trace_from == -1) h->trace_from = getenv("SPHSM_TRACE") ? atoi(getenv("SPHSM_TRACE")) : -2;
+    return h->trace_from >= 0 && h->total_steps >= h->trace_from && h->total_steps < h->trace_from + 3;
+}
+static void trace_mark(sphsm_handle *h, const char *label, bool side = false) {
+    if (!trace_on(h)) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, side ? h->side_stream : h->stream);
+    h->trace.push_back({e, label, side ? 1 : 0});
+}
+static void trace_dump(sphsm_handle *h) {
+    if (h->trace.empty() || h->total_steps != h->trace_from + 3) return;
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->side_stream);
+    if (h->rank == 0 || h->rank == h->nranks - 1 || h->rank == h->nranks / 2) {
+        std::string out = "[sphsm trace rank " + std::to_string(h->rank) + "] us since the first mark (M = main stream, S = side stream)\n";
+        for (auto &t : h->trace) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->trace[0].ev, t.ev);
+            char b[160];
+            snprintf(b, sizeof b, "  %9.1f %s %s\n", ms * 1e3, t.stream ? "S" : "M", t.label);
+            out += b;
+        }
+        fputs(out.c_str(), stderr);
+    }
+    for (auto &t : h->trace) cudaEventDestroy(t.ev);
+    h->trace.clear();
+}
+
 // ---- the slab step as phases; every phase ends in the collective named by *coll ----------------------------------------
 enum { COLL_NONE = 0, COLL_EXCH1, COLL_ALLREDUCE, COLL_EXCH2, COLL_DONE, COLL_ALLREDUCE_MOMENTS, COLL_EXCH1_TAKEN, COLL_EXCH1_EARLY };
 static const int MG_PHASES = 7;
@@ -327,6 +358,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 if ((rc = slab_check_local_error(h)) != 0) return rc;  // (NCCL ranks stop together, through the allreduced flag)
             }
             h->moments_forked = false;
+            trace_mark(h, "step begin");
             if (h->comm_mode == 1 && !h->rest_dirty && !h->profiling) {
                 // the moment sums, their allreduce and the solve only need last step's owned slots: they run on the side
                 // stream beside the exchange, the hash and the sort, and rejoin before the gather applies the transform
@@ -338,6 +370,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 rc = moments_part(h);
                 h->launch_stream = h->stream;
                 if (rc) return rc;
+                trace_mark(h, "moment sums done", true);
                 h->moments_forked = true;
                 h->allreduce_pending = true;
                 if (h->nccl_comm_red != h->nccl_comm) {  // own communicator: nothing to queue behind
@@ -363,6 +396,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 h->launch_stream = h->stream;
                 if (rc) return rc;
                 CU(cudaStreamWaitEvent(h->stream, h->ev_x1, 0));
+                trace_mark(h, "halos dropped, early exchange 1 awaited");
                 if (h->gt) h->gt->end_group(KG_OTHER);
                 *coll = COLL_EXCH1_TAKEN;
                 return SPHSM_OK;
@@ -386,16 +420,20 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             // host waits for the boundaries, i.e. in every step whose rest-state sums need the extent below.)
             h->mom_n = h->n + 2 * cap;
             if (h->gt) h->gt->end_group(KG_OTHER);
+            trace_mark(h, "unpacked");
             if ((rc = grid_sort(h, h->gt, &prev->n_live, 2 * cap, h->n_bound + 2 * cap)) != 0) return rc;
+            trace_mark(h, "sorted");
             h->reordered = false;
             const int nacc = h->dp.quadratic ? 33 : 15;
             if (h->moments_forked) {
                 // the forked chain has delivered the transform and the summed error flag: plane boundaries + flag -> SlabMeta,
                 // then the gather, which takes the live count from there
                 CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+                trace_mark(h, "transform joined");
                 h->moments_forked = false;
                 if ((rc = slab_meta_launch(h, h->totals + nacc)) != 0) return rc;
                 if ((rc = grid_finish(h, h->gt, diag ? 2 : 1, true, &h->d_meta[h->meta_cur]->n_live, h->n_bound + 2 * cap)) != 0) return rc;
+                trace_mark(h, "gathered");
                 h->reordered = true;
             } else {
                 if ((rc = slab_meta_launch(h, nullptr)) != 0) return rc;
@@ -453,14 +491,18 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 if (!rc) rc = pack2(h);
                 h->launch_stream = h->stream;
                 if (rc) return rc;
+                trace_mark(h, "pass A boundary + pack2 done", true);
                 CU(cudaEventRecord(h->ev_bnd, h->side_stream));
                 if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_int)) != 0) return rc;  // (queued before the NCCL calls: they take host time)
                 CU(cudaEventRecord(h->ev_int, h->stream));
+                trace_mark(h, "pass A interior done");
                 // pass B is cut two planes deep: the planes at least two away from a face read no boundary-plane record at all, so
                 // they follow pass A's interior directly; the two outer planes of either side wait for exchange 2 on the side stream
                 if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_int2)) != 0) return rc;
                 if (g_host_prof_early() && h->pev[4]) CU(cudaEventRecord(h->pev[4], h->side_stream));
+                trace_mark(h, "pass B inner planes done");
                 rc = nccl_exchange2(h, h->side_stream);
+                trace_mark(h, "exchange 2 done", true);
                 if (g_host_prof_early() && h->pev[5]) CU(cudaEventRecord(h->pev[5], h->side_stream));
                 return rc;
             }
@@ -487,6 +529,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 }();
                 h->launch_stream = h->stream;
                 if (rc) return rc;
+                trace_mark(h, "pass B outer planes + classify done", true);
                 *coll = COLL_EXCH1_EARLY;
                 return SPHSM_OK;
             }
@@ -496,8 +539,10 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
         }
         case 6: {  // the two streams meet; bookkeeping
             if (h->split) {
+                trace_mark(h, "early exchange 1 done", true);
                 CU(cudaEventRecord(h->ev_join, h->side_stream));
                 CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+                trace_mark(h, "step end (streams joined)");
             }
             std::swap(h->cur.P, h->alt.P);
             if (h->gt) {
@@ -512,6 +557,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             h->goal_pv_stale = !diag;
             h->prev_vel_valid = true;
             h->total_steps++;
+            trace_dump(h);
             *coll = COLL_DONE;
             return SPHSM_OK;
         }
@@ -529,9 +575,11 @@ static int mg_check(sphsm_handle *h) {
 static int mg_forked_allreduce(sphsm_handle *h) {
     h->launch_stream = h->side_stream;
     int rc = moment_allreduce(h);
+    trace_mark(h, "allreduce done", true);
     if (!rc) rc = [&]() -> int { LAUNCH(k_sm_solve, 1, 1, h->dp, h->totals, h->sm); return SPHSM_OK; }();
     h->launch_stream = h->stream;
     if (rc) return rc;
+    trace_mark(h, "solve done", true);
     CU(cudaEventRecord(h->ev_join, h->side_stream));
     return SPHSM_OK;
 }

@@ -81,6 +81,12 @@ __device__ __forceinline__ int list_get(unsigned addr) {
 #define SPHSM_PT4 128  // measured at 8M (pass A / pass B us): 64: 484 / 689, 128: 469 / 678, 256: 497 / 692, 512: 523 / 720
 #endif
 constexpr int PT4 = SPHSM_PT4;        // threads per block of the generation-4 passes
+#ifndef SPHSM_A_MINB
+#define SPHSM_A_MINB 9  // resident blocks per SM pass A / pass B are compiled for: 56 / 64 registers (measured in round 2 against 8 / 7: see DESIGN.md)
+#endif
+#ifndef SPHSM_B_MINB
+#define SPHSM_B_MINB 8
+#endif
 constexpr unsigned LSTEP = 4u * PT4;  // bytes between consecutive entries of one lane
 // Likewise a gathered array's base pointer: `pinned(ptr, zero)` is ptr + 0 with the zero coming from global memory, formed
 // in PTX so that neither the front end (which would fold it into the index) nor ptxas (which would re-load the kernel
@@ -237,7 +243,7 @@ __device__ __forceinline__ void pass_a4_one(const DevParams &p, const DevParams 
 // RNG: the launch range comes from device memory (slab step).  A template parameter, not a run-time test: with the test compiled
 // in, the single-GPU kernel kept 48 bytes of spills at its 56 registers and lost 10 % (ncu r02: 520 us against 470).
 template <bool RNG>
-__global__ void __launch_bounds__(PT4, 1152 / PT4) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+__global__ void __launch_bounds__(PT4, SPHSM_A_MINB) k_pass_a4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 const int *__restrict__ cell_start, const uint32_t *__restrict__ skey, const int *__restrict__ rng) {
     __shared__ int s_list[LIST_K * PT4];
     int i;
@@ -435,7 +441,7 @@ __device__ __forceinline__ void pass_b4_one(const DevParams &p, const DevParams 
     pass_b_finish<DIAG>(p, a, Pout, i, pi, vi, e4, si.y, fixed, ax, ay, az, L + L1, inv_mass, next_keys, next_rank, cell_count);
 }
 template <bool DIAG, bool RNG>
-__global__ void __launch_bounds__(PT4, 1024 / PT4) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
+__global__ void __launch_bounds__(PT4, SPHSM_B_MINB) k_pass_b4(const __grid_constant__ DevParams p, const DevParams *__restrict__ g, Arrays a,
                                                 float4 *__restrict__ Pout, const int *__restrict__ cell_start, const uint32_t *__restrict__ skey,
                                                 uint32_t *__restrict__ next_keys, uint32_t *__restrict__ next_rank, uint32_t *__restrict__ cell_count,
                                                 const int *__restrict__ rng) {

@@ -451,7 +451,8 @@ def run_ours(args, wl, rank, world_size, local_rank):
             roofline["traffic"] = tr.get("dram_bytes_per_launch")
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------------------
-    own_cap = n_total if world_size == 1 else min(n_total, int(n_local * 1.25) + 65536)  # owned counts drift with migration
+    # the owned count is only known on the device, so a fixed window crosses PCIe: what the library bounds the count by
+    own_cap = n_total if world_size == 1 else min(n_total, n_local + 2 * sim.comm_info()["halo_capacity"] + 4096)
     stim_by_id = stim.copy()
     stim_host = torch.zeros((own_cap,), dtype=torch.float32).pin_memory()
     pos_host = torch.empty((own_cap, 3), dtype=torch.float32).pin_memory()
@@ -513,8 +514,8 @@ def run_ours(args, wl, rank, world_size, local_rank):
            "protocol": ("per step: sphsm_set_masks_async(stim, 4 B per particle) from pinned host memory -> sphsm_step(1) -> "
                         "sphsm_download_positions_async (12 B per particle)" if world_size == 1 else
                         "per step and rank: sphsm_set_stim_owned_async (stimulation of the rank's own particles, 4 B each, pinned host memory) -> "
-                        "sphsm_step(1) -> sphsm_download_owned_async (ids + positions of the rank's particles, 16 B each, a fixed 1.25 x slab-sized "
-                        "window because the owned count is only known on the device)")
+                        "sphsm_step(1) -> sphsm_download_owned_async (ids + positions of the rank's particles, 16 B each, a fixed window of the slab's "
+                        "population bound because the owned count is only known on the device)")
                        + " to pinned host memory; copies overlap the next step on the library's copy streams, the timed region "
                          "ends when the last result is in host memory (sphsm_sync); bytes summed over ranks"}
     assert np.isfinite(pos_host.numpy()[:n_read]).all()

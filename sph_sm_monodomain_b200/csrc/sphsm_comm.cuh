@@ -255,9 +255,6 @@ __global__ void __launch_bounds__(256) k_mg_unpack2(const SlabMeta *__restrict__
     }
 }
 
-// the rank's error state as one double for the moment allreduce: every rank learns in the same step that some rank failed
-__global__ void k_store_flag(double *dst, const int *__restrict__ err) { *dst = (err[0] | err[1] | err[2]) ? 1.0 : 0.0; }
-
 // compact (id, xyz) of the owned slots for sphsm_download_owned; the range comes from device memory (rng = {begin, end}) and the
 // count is left in *count_out for the asynchronous form
 __global__ void __launch_bounds__(256) k_mg_owned_out(const int *__restrict__ rng, int first_h, int count_h, int cap, Arrays a, int *__restrict__ ids,

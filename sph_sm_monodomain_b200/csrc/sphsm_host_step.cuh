@@ -192,8 +192,8 @@ static int moments_part(sphsm_handle *h) {
     if (h->dp.quadratic) LAUNCH(k_moments<9>, B, 256, d, h->cur.P, h->cur.O, h->sm, h->partial, rng);
     else LAUNCH(k_moments<3>, B, 256, d, h->cur.P, h->cur.O, h->sm, h->partial, rng);
     const int nacc = h->dp.quadratic ? 33 : 15;
-    LAUNCH(k_sum_partials_par, nacc, 256, h->partial, B, nacc, h->totals);
-    if (h->comm_mode == 1) LAUNCH(k_store_flag, 1, 1, h->totals + nacc, h->d_err);  // the rank's error state rides on the allreduce
+    if (h->comm_mode == 1) LAUNCH(k_sum_partials_par, nacc + 1, 256, h->partial, B, nacc, h->totals, (const int *)h->d_err);  // + the rank's error state: it rides on the allreduce
+    else LAUNCH(k_sum_partials_par, nacc, 256, h->partial, B, nacc, h->totals, (const int *)nullptr);
     return SPHSM_OK;
 }
 // the per-step moment allreduce (NCCL mode: + the summed error flag, which the sort's k_mg_meta passes on to the host read-back)

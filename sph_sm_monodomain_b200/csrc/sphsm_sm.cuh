@@ -497,9 +497,16 @@ __global__ void __launch_bounds__(256) k_reorder_goal(const __grid_constant__ De
 }
 
 // totals[k] = sum over blocks of partial[b * nacc + k]; one block per accumulator, fixed order (deterministic)
-__global__ void __launch_bounds__(256) k_sum_partials_par(const double *__restrict__ partial, int blocks, int nacc, double *totals) {
+// err != nullptr: one more block (blockIdx.x == nacc) stores the rank's error state as totals[nacc] for the moment allreduce of the
+// slab step (every rank learns in the same step that some rank failed)
+__global__ void __launch_bounds__(256) k_sum_partials_par(const double *__restrict__ partial, int blocks, int nacc, double *totals,
+                                                          const int *__restrict__ err = nullptr) {
     __shared__ double s[256];
     const int k = blockIdx.x;
+    if (k == nacc) {
+        if (threadIdx.x == 0) totals[nacc] = (err[0] | err[1] | err[2]) ? 1.0 : 0.0;
+        return;
+    }
     double v = 0.0;
     for (int b = threadIdx.x; b < blocks; b += 256) v += partial[(size_t)b * nacc + k];
     s[threadIdx.x] = v;

@@ -221,6 +221,10 @@ const char *sphsm_kernel_group_name(int group);
  * From then on sphsm_step includes the halo / migrant exchange (ncclSend / ncclRecv with the two slab neighbours) and
  * the shape-matching moment allreduce, particle ids stay global, and download_aos / download_positions write only the
  * particles this rank owns (n = global count).  params.reserved[0] overrides the per-message halo capacity.
+ * The step never waits for the host: a step error (halo message overflow, a particle crossing two cell planes) is returned by
+ * sphsm_step on EVERY rank at the same step, two to three steps after it happened.  Calls that change particle state between
+ * steps (set_masks*, stim_*, set_stim*, uploads) are COLLECTIVE in slab mode: all ranks issue the same calls in the same order
+ * (the next step's halo exchange may already be under way and is repeated on every rank alike when such a call voids it).
  * NCCL is resolved at run time (dlopen "libnccl.so.2", or $SPHSM_NCCL_LIB). */
 int sphsm_comm_unique_id(void *id128);
 int sphsm_comm_init(sphsm_handle *h, int nranks, int rank, const void *id128);

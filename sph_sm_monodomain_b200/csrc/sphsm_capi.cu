@@ -148,8 +148,9 @@ struct sphsm_handle {
     // planes are still being integrated).  Anything that changes particle state other than stimulation values between two steps
     // voids it (x1_early_valid = false): the next step then classifies and exchanges again, on every rank alike — state mutators
     // are collective calls in slab mode.
-    bool x1_early_pending = false, x1_early_valid = false;
-    cudaEvent_t ev_x1 = nullptr;
+    bool x1_early_pending = false, x1_early_valid = false, check_interior_pending = false;
+    cudaEvent_t ev_x1 = nullptr, ev_meta_ready = nullptr;
+    cudaStream_t meta_stream = nullptr;  // the 32-byte read-backs of SlabMeta travel beside the step, not inside its main stream
     int b2 = 0, b3 = 0;       // start of the 2nd / of the last owned plane, as of the last applied read-back
     int n_global = 0;         // particles uploaded before sphsm_comm_set_slab filtered them (ids are global)
     int mom_n = 0;            // slab step: extent of the PRE-reorder arrays (old slots + both message regions) the REST-state sums scan
@@ -424,6 +425,8 @@ static int create_impl(const sphsm_params *p, sphsm_handle **out, sphsm_handle *
     for (cudaEvent_t *e : {&h->ev_in_ready, &h->ev_in_free, &h->ev_out_ready, &h->ev_out_done}) CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_bnd, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_x1, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_meta_ready, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&h->meta_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming));
     h->launch_stream = h->stream;
     if ((rc = alloc_arrays(h, h->cur, cap, true)) != 0) return rc;
@@ -497,6 +500,8 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     cudaFree(h->io_in_f); cudaFree(h->io_in_b); cudaFree(h->io_out_f); cudaFree(h->io_out_i);
     if (h->ev_bnd) cudaEventDestroy(h->ev_bnd);
     if (h->ev_x1) cudaEventDestroy(h->ev_x1);
+    if (h->ev_meta_ready) cudaEventDestroy(h->ev_meta_ready);
+    if (h->meta_stream) cudaStreamDestroy(h->meta_stream);
     if (h->ev_int) cudaEventDestroy(h->ev_int);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);

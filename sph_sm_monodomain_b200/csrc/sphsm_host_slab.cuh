@@ -140,10 +140,15 @@ static int slab_meta_launch(sphsm_handle *h, const double *flag_src) {
     const DevParams &d = h->dp;
     if (h->meta_issued - h->meta_consumed >= sphsm_handle::META_RING) return fail(h, SPHSM_ERR_COMM, "internal: slab read-back ring overrun");
     h->meta_cur ^= 1;
+    // (this buffer was last read back two sorts ago: its copy has long left, the wait is for form)
+    if (h->meta_issued >= 2) CU(cudaStreamWaitEvent(h->launch_stream, h->ev_ring[(h->meta_issued - 2) % sphsm_handle::META_RING], 0));
     LAUNCH(k_mg_meta, 1, 32, h->cell_start, d.num_cells, d.ga * d.gb, d.gcl, h->d_err, flag_src, h->n_bound, h->d_meta[h->meta_cur]);
+    // the read-back runs on its own stream: a copy inside the main stream held the gather back by 6-8 us (SPHSM_TRACE at 8 GPUs)
     const int slot = (int)(h->meta_issued % sphsm_handle::META_RING);
-    CU(cudaMemcpyAsync(h->h_ring + 8 * slot, h->d_meta[h->meta_cur], 8 * sizeof(int), cudaMemcpyDeviceToHost, h->launch_stream));
-    CU(cudaEventRecord(h->ev_ring[slot], h->launch_stream));
+    CU(cudaEventRecord(h->ev_meta_ready, h->launch_stream));
+    CU(cudaStreamWaitEvent(h->meta_stream, h->ev_meta_ready, 0));
+    CU(cudaMemcpyAsync(h->h_ring + 8 * slot, h->d_meta[h->meta_cur], 8 * sizeof(int), cudaMemcpyDeviceToHost, h->meta_stream));
+    CU(cudaEventRecord(h->ev_ring[slot], h->meta_stream));
     h->meta_issued++;
     return SPHSM_OK;
 }
@@ -383,18 +388,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 // and nothing in the interior may sit where it should have been sent from (checked beside the sums)
                 h->x1_early_pending = false;
                 LAUNCH(k_mg_drop_halos, cdiv(2 * cap, 256), 256, h->cur, h->d_meta[h->meta_cur], cap);
-                h->launch_stream = h->side_stream;
-                rc = [&]() -> int {
-                    if (!h->moments_forked) {  // (the side stream is not forked in this step: order it behind the main stream first)
-                        CU(cudaEventRecord(h->ev_fork, h->stream));
-                        CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-                    }
-                    LAUNCH(k_mg_check_interior, cdiv(std::max(h->own_bound, 1), 256), 256, h->dp, h->cur.P, h->d_meta[h->meta_cur], has_left ? 1 : 0,
-                           has_right ? 1 : 0, h->d_err);
-                    return SPHSM_OK;
-                }();
-                h->launch_stream = h->stream;
-                if (rc) return rc;
+                h->check_interior_pending = true;  // (queued behind the allreduce + solve: see mg_check_interior)
                 CU(cudaStreamWaitEvent(h->stream, h->ev_x1, 0));
                 trace_mark(h, "halos dropped, early exchange 1 awaited");
                 if (h->gt) h->gt->end_group(KG_OTHER);
@@ -498,6 +492,9 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 trace_mark(h, "pass A interior done");
                 // pass B is cut two planes deep: the planes at least two away from a face read no boundary-plane record at all, so
                 // they follow pass A's interior directly; the two outer planes of either side wait for exchange 2 on the side stream
+                // (they do not need the boundary planes' records, but everything queued on the side stream before them — the interior
+                // check reads the buffer pass B is about to overwrite with the new positions — must have finished: ev_bnd is long past)
+                CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
                 if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_int2)) != 0) return rc;
                 if (g_host_prof_early() && h->pev[4]) CU(cudaEventRecord(h->pev[4], h->side_stream));
                 trace_mark(h, "pass B inner planes done");
@@ -565,6 +562,26 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
     return fail(h, SPHSM_ERR_INVALID, "bad phase");
 }
 
+// beside the sort, on the side stream BEHIND the moment chain (in front of it, it delayed the allreduce by its own 8 us)
+static int mg_check_interior(sphsm_handle *h) {
+    if (!h->check_interior_pending) return SPHSM_OK;
+    h->check_interior_pending = false;
+    const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
+    if (!h->moments_forked) {  // (the side stream is not forked in this step: order it behind the main stream first)
+        CU(cudaEventRecord(h->ev_fork, h->stream));
+        CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    }
+    h->launch_stream = h->side_stream;
+    // (h->meta_cur still names the previous layout here: the sort of this step has not been queued yet)
+    int rc = [&]() -> int {
+        LAUNCH(k_mg_check_interior, cdiv(std::max(h->own_bound, 1), 256), 256, h->dp, h->cur.P, h->d_meta[h->meta_cur], has_left ? 1 : 0, has_right ? 1 : 0,
+               h->d_err);
+        return SPHSM_OK;
+    }();
+    h->launch_stream = h->stream;
+    return rc;
+}
+
 static int mg_check(sphsm_handle *h) {
     if (!h->slab_applied) return fail(h, SPHSM_ERR_COMM, "sphsm_comm_set_slab must be applied after the particle set is uploaded");
     if (h->stage_timing) return fail(h, SPHSM_ERR_INVALID, "stage timing is single-GPU only");
@@ -617,6 +634,7 @@ static int mg_step_nccl(sphsm_handle *h) {
         else if (coll == COLL_EXCH1_TAKEN) {  // the exchange happened at the end of the previous step: only the allreduce is left
             if (h->moments_forked && h->allreduce_pending) rc = mg_forked_allreduce(h);
             h->allreduce_pending = false;
+            if (!rc) rc = mg_check_interior(h);
         } else if (coll == COLL_EXCH1_EARLY) {  // next step's exchange 1, on the side stream behind the outer planes' pass B
             rc = nccl_exchange1(h, h->side_stream);
             if (!rc) CU(cudaEventRecord(h->ev_x1, h->side_stream));

@@ -232,6 +232,10 @@ int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi);
 /* out: [0] comm mode (0 none, 1 NCCL, 2 local group) [1] nranks [2] rank [3] local slots (owned + halo)
  *      [4] first owned slot [5] end of owned slots [6] halo message capacity [7] slab mode on */
 int sphsm_comm_info(sphsm_handle *h, int out8[8]);
+/* Exchange-1 message capacities (particles) of the exchange packed last: [0] to left [1] to right [2] from left [3] from right.
+ * They follow the face populations of three exchanges earlier (a quarter + 2048 particles of margin, at most the halo capacity;
+ * full capacity after every upload / new slab); sphsm_tune("x1_dynamic", 0) pins them to the halo capacity. */
+int sphsm_comm_x1_sizes(sphsm_handle *h, int out4[4]);
 /* Compact read-back of the owned particles: original ids and positions (3 floats each); *count = owned particles. */
 int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int cap, int *count);
 /* Virtual ranks for testing the slab logic on ONE device: nranks handles (same device, capacity, world, slab_axis) form

@@ -151,6 +151,13 @@ struct sphsm_handle {
     bool x1_early_pending = false, x1_early_valid = false, check_interior_pending = false;
     cudaEvent_t ev_x1 = nullptr, ev_meta_ready = nullptr;
     cudaStream_t meta_stream = nullptr;  // the 32-byte read-backs of SlabMeta travel beside the step, not inside its main stream
+    // exchange-1 messages are sized from the populations both sides of a face saw X1_LAG exchanges ago (see x1_plan)
+    static constexpr int X1_RING = 8, X1_LAG = 3;
+    int x1_send_cap[2] = {0, 0}, x1_recv_cap[2] = {0, 0};  // particles per message of the exchange packed last (<= send_cap)
+    long long x1_seq = 0, x1_floor = 0;                    // exchanges packed so far / the first one after the last population change
+    int *d_x1rec = nullptr, *h_x1rec = nullptr;            // X1_RING x {sent left, sent right, received left, received right}; pinned copy
+    long long x1rec_seq[X1_RING] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    cudaEvent_t ev_x1rec[X1_RING] = {}, ev_x1rec_ready = nullptr;
     int b2 = 0, b3 = 0;       // start of the 2nd / of the last owned plane, as of the last applied read-back
     int n_global = 0;         // particles uploaded before sphsm_comm_set_slab filtered them (ids are global)
     int mom_n = 0;            // slab step: extent of the PRE-reorder arrays (old slots + both message regions) the REST-state sums scan
@@ -171,8 +178,8 @@ struct sphsm_handle {
 
 // SPHSM_SYNC_DEBUG=1 in the environment synchronises after every launch and names the kernel that faulted
 static const bool g_sync_debug = getenv("SPHSM_SYNC_DEBUG") != nullptr;
-// SPHSM_PASS selects the fast-path neighbour passes: 6 = sphsm_pass6.cuh (production: block-staged stencil spans), 4 = the gathered
-// thread-per-particle passes of sphsm_pass4.cuh (the bit-identical reference the staged passes are tested against).
+// SPHSM_PASS selects the fast-path neighbour passes: 4 = the gathered thread-per-particle passes of sphsm_pass4.cuh (production),
+// 6 = sphsm_pass6.cuh (block-staged stencil spans: bit-identical, measured slower, kept as the documented experiment).
 // SPHSM_STAGE6=0 makes every block of the generation-6 kernels take their in-kernel gathered path; SPHSM_T6 = 64 | 128 targets per
 // block; SPHSM_B_STEP6 = 2 | 4 candidates per iteration of pass B's phase 1.
 // The same four switches can be changed at run time with sphsm_tune("pass" | "stage6" | "t6" | "b_step6", value) (tests).
@@ -180,6 +187,9 @@ static int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 4;
 static int g_stage6 = getenv("SPHSM_STAGE6") ? atoi(getenv("SPHSM_STAGE6")) : 1;
 static int g_t6 = getenv("SPHSM_T6") ? atoi(getenv("SPHSM_T6")) : 128;
 static int g_b_step6 = getenv("SPHSM_B_STEP6") ? atoi(getenv("SPHSM_B_STEP6")) : 2;
+// 1: exchange-1 messages sized from the lagged face populations; 0: always the full halo capacity.  Process-wide: every rank of a group
+// must run with the same setting (the two sides of a face derive the message size from it)
+static int g_x1_dynamic = getenv("SPHSM_X1_DYNAMIC") ? atoi(getenv("SPHSM_X1_DYNAMIC")) : 1;
 static int g_warp_path = getenv("SPHSM_WARP_PATH") ? atoi(getenv("SPHSM_WARP_PATH")) : 1;  // 0: small dense sets take the thread-per-particle kernels too
 extern "C" int sphsm_tune(const char *name, int value) {
     if (!name) return SPHSM_ERR_INVALID;
@@ -189,6 +199,7 @@ extern "C" int sphsm_tune(const char *name, int value) {
     else if (n == "t6" && (value == 64 || value == 128)) g_t6 = value;
     else if (n == "b_step6" && (value == 2 || value == 4)) g_b_step6 = value;
     else if (n == "warp_path" && (value == 0 || value == 1)) g_warp_path = value;
+    else if (n == "x1_dynamic" && (value == 0 || value == 1)) g_x1_dynamic = value;
     else return SPHSM_ERR_INVALID;
     return SPHSM_OK;
 }
@@ -427,6 +438,8 @@ static int create_impl(const sphsm_params *p, sphsm_handle **out, sphsm_handle *
     CU(cudaEventCreateWithFlags(&h->ev_x1, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_meta_ready, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&h->meta_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_x1rec_ready, cudaEventDisableTiming));
+    for (int k = 0; k < sphsm_handle::X1_RING; k++) CU(cudaEventCreateWithFlags(&h->ev_x1rec[k], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_int, cudaEventDisableTiming));
     h->launch_stream = h->stream;
     if ((rc = alloc_arrays(h, h->cur, cap, true)) != 0) return rc;
@@ -502,6 +515,11 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     if (h->ev_x1) cudaEventDestroy(h->ev_x1);
     if (h->ev_meta_ready) cudaEventDestroy(h->ev_meta_ready);
     if (h->meta_stream) cudaStreamDestroy(h->meta_stream);
+    if (h->ev_x1rec_ready) cudaEventDestroy(h->ev_x1rec_ready);
+    for (int k = 0; k < sphsm_handle::X1_RING; k++)
+        if (h->ev_x1rec[k]) cudaEventDestroy(h->ev_x1rec[k]);
+    if (h->d_x1rec) cudaFree(h->d_x1rec);
+    if (h->h_x1rec) cudaFreeHost(h->h_x1rec);
     if (h->ev_int) cudaEventDestroy(h->ev_int);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -790,6 +808,7 @@ static void state_changed(sphsm_handle *h, bool rest) {
     h->inter_live = true;
     h->prev_vel_valid = false;
     h->x1_early_valid = false;
+    h->x1_floor = h->x1_seq;  // the populations may have changed: full-size messages until X1_LAG fresh exchanges have been seen
     if (rest) {
         h->goal_pv_stale = false;  // uploads / Init_Fluid write GOAL, PV and their frozen copies
         h->rest_dirty = true;
@@ -985,6 +1004,7 @@ extern "C" int sphsm_set_masks(sphsm_handle *h, const uint8_t *fixed, const floa
     return SPHSM_OK;
 }
 
+static void trace_mark(sphsm_handle *h, const char *label, bool side = false);  // SPHSM_TRACE (sphsm_host_slab.cuh)
 #include "sphsm_host_io.cuh"    // snapshot / restart, asynchronous per-frame I/O
 #include "sphsm_host_step.cuh"  // timers, neighbour grid, shape-matching sums, staged / fused step, graph replay
 

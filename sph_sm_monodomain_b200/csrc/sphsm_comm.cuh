@@ -7,7 +7,7 @@
 //   k_mg_classify   stale halos are marked dead; owned particles whose NEW plane is the first / last owned plane or
 //                   beyond are copied into the message for that neighbour (halo refresh and migration are the same
 //                   message: the receiver's hash decides ownership) and stay here (as owned or as halo)
-//   exchange 1      fixed-capacity messages (count in the header), ncclSend / ncclRecv
+//   exchange 1      messages with the count in the header, sized from the lagged face populations (x1_plan), ncclSend / ncclRecv
 //   k_mg_unpack     arrivals are appended behind the local particles; unused message slots become dead entries that the
 //                   sort pushes into the limbo bucket
 //   ... hash, sort (canonical in-cell order = ascending original index, so both sides of a slab face hold that plane in
@@ -98,7 +98,7 @@ __device__ __forceinline__ void msg_put(const MsgView &m, int k, const Arrays &a
 
 // err[0]: particles that crossed more than one plane in a step; err[1]: message overflow / face population mismatch
 __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ DevParams p, Arrays a, int has_left, int has_right, MsgView L,
-                                                     MsgView R, int cap, int *err, const SlabMeta *__restrict__ m) {
+                                                     MsgView R, int capL, int capR, int *err, const SlabMeta *__restrict__ m) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= m->n_live) return;
     if (s < m->own_begin || s >= m->own_end) {  // last step's halo copy: the owner sends a fresh one
@@ -110,12 +110,12 @@ __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ Dev
     if ((has_left && pl < p.slab_lo - 1) || (has_right && pl > p.slab_hi) || pl == INT_MIN) atomicAdd(&err[0], 1);
     if (has_left && pl <= p.slab_lo) {
         const int k = atomicAdd(L.count, 1);
-        if (k < cap) msg_put(L, k, a, s, q);
+        if (k < capL) msg_put(L, k, a, s, q);
         else atomicAdd(&err[1], 1);
     }
     if (has_right && pl >= p.slab_hi - 1) {
         const int k = atomicAdd(R.count, 1);
-        if (k < cap) msg_put(R, k, a, s, q);
+        if (k < capR) msg_put(R, k, a, s, q);
         else atomicAdd(&err[1], 1);
     }
 }
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ Dev
 // explicitly: run right after pass B on the two outermost planes of either side, on the freshly integrated positions `Pnew`,
 // so that exchange 1 of the NEXT step travels while pass B still works on the interior planes.
 __global__ void __launch_bounds__(256) k_mg_classify_rng(const __grid_constant__ DevParams p, Arrays a, const float4 *__restrict__ Pnew,
-                                                         const int *__restrict__ rng, int has_left, int has_right, MsgView L, MsgView R, int cap,
-                                                         int *err) {
+                                                         const int *__restrict__ rng, int has_left, int has_right, MsgView L, MsgView R, int capL,
+                                                         int capR, int *err) {
     const int4 r = *reinterpret_cast<const int4 *>(rng);
     int s = r.x + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= r.z) s += r.w;
@@ -135,12 +135,12 @@ __global__ void __launch_bounds__(256) k_mg_classify_rng(const __grid_constant__
     if ((has_left && pl < p.slab_lo - 1) || (has_right && pl > p.slab_hi) || pl == INT_MIN) atomicAdd(&err[0], 1);
     if (has_left && pl <= p.slab_lo) {
         const int k = atomicAdd(L.count, 1);
-        if (k < cap) msg_put(L, k, a, s, q);
+        if (k < capL) msg_put(L, k, a, s, q);
         else atomicAdd(&err[1], 1);
     }
     if (has_right && pl >= p.slab_hi - 1) {
         const int k = atomicAdd(R.count, 1);
-        if (k < cap) msg_put(R, k, a, s, q);
+        if (k < capR) msg_put(R, k, a, s, q);
         else atomicAdd(&err[1], 1);
     }
 }
@@ -163,16 +163,26 @@ __global__ void __launch_bounds__(256) k_mg_check_interior(const __grid_constant
 
 // arrivals -> slots [n0, n0 + 2*cap), n0 = the live count before this step's exchange: left message first; unused slots are dead.
 // A message whose header count exceeds the capacity was truncated by its sender: the receiver flags it in the same step.
+// capL / capR: the capacity this exchange's messages were laid out for (<= cap, see x1_plan).  Thread 0 files the populations of the
+// exchange — what this rank sent (its send headers are still intact) and what it received — for the sizing of a later one.
 __global__ void __launch_bounds__(256) k_mg_unpack(const SlabMeta *__restrict__ prev, Arrays a, int has_left, int has_right, MsgView L, MsgView R,
-                                                   int cap, int *err) {
+                                                   int cap, int capL, int capR, int *err, const int *__restrict__ sentL, const int *__restrict__ sentR,
+                                                   int *__restrict__ rec) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) {
+        rec[0] = has_left ? *sentL : 0;
+        rec[1] = has_right ? *sentR : 0;
+        rec[2] = has_left ? *L.count : 0;
+        rec[3] = has_right ? *R.count : 0;
+    }
     if (idx >= 2 * cap) return;
     const int n0 = prev->n_live;
     const int side = idx >= cap, k = idx - side * cap, slot = n0 + idx;
     const MsgView &m = side ? R : L;
+    const int mcap = side ? capR : capL;
     const int sent = (side ? has_right : has_left) ? *m.count : 0;
-    if (k == 0 && sent > cap) atomicAdd(&err[1], 1);
-    const int cnt = min(sent, cap);
+    if (k == 0 && sent > mcap) atomicAdd(&err[1], 1);
+    const int cnt = min(sent, mcap);
     if (k < cnt) {
         a.P[slot] = m.P[k];
         a.VEL[slot] = m.VEL[k];

@@ -72,6 +72,10 @@ static int comm_alloc(sphsm_handle *h) {
         CU(cudaMemset(h->d_meta[k], 0, sizeof(SlabMeta)));
     }
     CU(cudaMalloc(&h->d_count, sizeof(int)));
+    CU(cudaMalloc(&h->d_x1rec, sphsm_handle::X1_RING * 4 * sizeof(int)));
+    CU(cudaMemset(h->d_x1rec, 0, sphsm_handle::X1_RING * 4 * sizeof(int)));
+    CU(cudaMallocHost(&h->h_x1rec, sphsm_handle::X1_RING * 4 * sizeof(int)));
+    h->x1_send_cap[0] = h->x1_send_cap[1] = h->x1_recv_cap[0] = h->x1_recv_cap[1] = cap;
     CU(cudaMallocHost(&h->h_ring, sphsm_handle::META_RING * 8 * sizeof(int)));
     for (auto &e : h->ev_ring) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return SPHSM_OK;
@@ -211,6 +215,7 @@ extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
     // keep only the owned planes: dead entries sort into the limbo bucket and fall off the end
     h->local_error = 0; h->peer_error = false; h->failed = false;
     h->x1_early_pending = false; h->x1_early_valid = false;
+    h->x1_floor = h->x1_seq;
     h->meta_consumed = h->meta_issued;  // (read-backs of an earlier slab are void)
     if (h->d_err) CU(cudaMemsetAsync(h->d_err, 0, 4 * sizeof(int), h->stream));
     h->n_bound = h->alloc_n;
@@ -226,6 +231,12 @@ extern "C" int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi) {
     }
     h->grid_valid = false;
     h->slab_applied = true;
+    return SPHSM_OK;
+}
+
+extern "C" int sphsm_comm_x1_sizes(sphsm_handle *h, int out[4]) {
+    if (!h || !out) return SPHSM_ERR_INVALID;
+    out[0] = h->x1_send_cap[0]; out[1] = h->x1_send_cap[1]; out[2] = h->x1_recv_cap[0]; out[3] = h->x1_recv_cap[1];
     return SPHSM_OK;
 }
 
@@ -262,16 +273,56 @@ static int comm_allreduce(sphsm_handle *h, int count) {
     NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm_red, h->launch_stream));
     return SPHSM_OK;
 }
+// Exchange-1 message sizes.  A message carries one cell plane's worth of particles (plus migrants), but how many that is only the
+// device knows; sending the full halo capacity every step cost 68 us per step at 8 GPUs / 8M particles (SPHSM_TRACE), 2-4 times
+// what the live entries need.  So every unpack files {sent left, sent right, received left, received right} of ITS exchange into a
+// small ring that is read back beside the step, and the exchange packed X1_LAG exchanges later is sized from it: my "sent right" of
+// exchange q is by construction my right neighbour's "received left" of exchange q (it is the header of the same message, and both
+// sides count exchanges alike because every exchange is a matched send / receive), so the two sides of a face always derive the
+// same size without talking to each other.  The margin (a quarter + 2048 particles over X1_LAG steps) is far above what a step
+// that moves no particle further than one cell plane can add; a message that overflows anyway is flagged like any halo overflow.
+// Population changes from outside (uploads, a new slab: collective by contract, like every mutator) reset the history.
+static int x1_plan(sphsm_handle *h) {
+    const int cap = h->send_cap;
+    const long long q = h->x1_seq++, src = q - sphsm_handle::X1_LAG;
+    for (int k = 0; k < 2; k++) h->x1_send_cap[k] = h->x1_recv_cap[k] = cap;
+    if (!g_x1_dynamic) return SPHSM_OK;
+    // the newest exchange at least X1_LAG back that was unpacked (one voided by a mutator before its unpack left no record: on
+    // every rank alike) and is still in the ring
+    int slot = -1;
+    for (long long c = src; c >= 0 && c >= h->x1_floor && c > q - sphsm_handle::X1_RING; c--)
+        if (h->x1rec_seq[c % sphsm_handle::X1_RING] == c) { slot = (int)(c % sphsm_handle::X1_RING); break; }
+    if (slot < 0) return SPHSM_OK;
+    CU(cudaEventSynchronize(h->ev_x1rec[slot]));  // X1_LAG is one more than the SlabMeta lag: the host has already waited for a later copy
+    const int *r = h->h_x1rec + 4 * slot;
+    auto sized = [cap](int c) {
+        const long long m = ((long long)c + c / 4 + 2048 + 255) / 256 * 256;
+        return (int)std::min<long long>(cap, m);
+    };
+    h->x1_send_cap[0] = sized(r[0]); h->x1_send_cap[1] = sized(r[1]);
+    h->x1_recv_cap[0] = sized(r[2]); h->x1_recv_cap[1] = sized(r[3]);
+    return SPHSM_OK;
+}
+// the record of the exchange that was just unpacked (k_mg_unpack wrote it) starts its way to the host
+static int x1_record_launch(sphsm_handle *h) {
+    const long long q = h->x1_seq - 1;
+    const int slot = (int)(q % sphsm_handle::X1_RING);
+    CU(cudaEventRecord(h->ev_x1rec_ready, h->launch_stream));
+    CU(cudaStreamWaitEvent(h->meta_stream, h->ev_x1rec_ready, 0));
+    CU(cudaMemcpyAsync(h->h_x1rec + 4 * slot, h->d_x1rec + 4 * slot, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->meta_stream));
+    CU(cudaEventRecord(h->ev_x1rec[slot], h->meta_stream));
+    h->x1rec_seq[slot] = q;
+    return SPHSM_OK;
+}
 static int nccl_exchange1(sphsm_handle *h, cudaStream_t st) {
-    const size_t bytes = msg_bytes(h->send_cap);
     NC(g_nccl.GroupStart());
     if (h->rank > 0) {
-        NC(g_nccl.Send(h->msg_send[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, st));
-        NC(g_nccl.Recv(h->msg_recv[0], bytes, NCCL_CHAR, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->msg_send[0], msg_bytes(h->x1_send_cap[0]), NCCL_CHAR, h->rank - 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->msg_recv[0], msg_bytes(h->x1_recv_cap[0]), NCCL_CHAR, h->rank - 1, h->nccl_comm, st));
     }
     if (h->rank < h->nranks - 1) {
-        NC(g_nccl.Send(h->msg_send[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, st));
-        NC(g_nccl.Recv(h->msg_recv[1], bytes, NCCL_CHAR, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Send(h->msg_send[1], msg_bytes(h->x1_send_cap[1]), NCCL_CHAR, h->rank + 1, h->nccl_comm, st));
+        NC(g_nccl.Recv(h->msg_recv[1], msg_bytes(h->x1_recv_cap[1]), NCCL_CHAR, h->rank + 1, h->nccl_comm, st));
     }
     NC(g_nccl.GroupEnd());
     return SPHSM_OK;
@@ -312,7 +363,7 @@ static bool trace_on(sphsm_handle *h) {
     if (h->trace_from == -1) h->trace_from = getenv("SPHSM_TRACE") ? atoi(getenv("SPHSM_TRACE")) : -2;
     return h->trace_from >= 0 && h->total_steps >= h->trace_from && h->total_steps < h->trace_from + 3;
 }
-static void trace_mark(sphsm_handle *h, const char *label, bool side = false) {
+static void trace_mark(sphsm_handle *h, const char *label, bool side) {
     if (!trace_on(h)) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
@@ -398,8 +449,10 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             h->x1_early_pending = false;  // (voided by a mutator: the messages are packed and exchanged again, on every rank alike)
             CU(cudaMemsetAsync(h->msg_send[0], 0, 16, h->stream));
             CU(cudaMemsetAsync(h->msg_send[1], 0, 16, h->stream));
-            LAUNCH(k_mg_classify, cdiv(std::max(h->n_bound, 1), 256), 256, h->dp, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_send[0], cap),
-                   msg_view(h->msg_send[1], cap), cap, h->d_err, h->d_meta[h->meta_cur]);
+            if ((rc = x1_plan(h)) != 0) return rc;
+            LAUNCH(k_mg_classify, cdiv(std::max(h->n_bound, 1), 256), 256, h->dp, h->cur, has_left ? 1 : 0, has_right ? 1 : 0,
+                   msg_view(h->msg_send[0], h->x1_send_cap[0]), msg_view(h->msg_send[1], h->x1_send_cap[1]), h->x1_send_cap[0], h->x1_send_cap[1],
+                   h->d_err, h->d_meta[h->meta_cur]);
             if (h->gt) h->gt->end_group(KG_OTHER);
             *coll = COLL_EXCH1;
             return SPHSM_OK;
@@ -407,8 +460,14 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
         case 1: {  // unpack arrivals, hash + sort everything, cell table, plane boundaries
             if (h->n_bound + 2 * cap > h->alloc_n) return fail(h, SPHSM_ERR_CAPACITY, "capacity too small for the halo arrivals");
             const SlabMeta *prev = h->d_meta[h->meta_cur];
-            LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, prev, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_recv[0], cap),
-                   msg_view(h->msg_recv[1], cap), cap, h->d_err);
+            {
+                const int slot = (int)((h->x1_seq - 1) % sphsm_handle::X1_RING);  // (its last read-back left X1_RING exchanges ago: a wait for form)
+                if (h->x1rec_seq[slot] >= 0) CU(cudaStreamWaitEvent(h->stream, h->ev_x1rec[slot], 0));
+                LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, prev, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_recv[0], h->x1_recv_cap[0]),
+                       msg_view(h->msg_recv[1], h->x1_recv_cap[1]), cap, h->x1_recv_cap[0], h->x1_recv_cap[1], h->d_err,
+                       (const int *)h->msg_send[0], (const int *)h->msg_send[1], h->d_x1rec + 4 * slot);
+                if ((rc = x1_record_launch(h)) != 0) return rc;
+            }
             // the entries to sort are the previous live slots + both message regions; the kernels read that count from `prev`,
             // the grids are sized for its upper bound.  (h->n itself is the host's last applied read-back: exact whenever the
             // host waits for the boundaries, i.e. in every step whose rest-state sums need the extent below.)
@@ -519,9 +578,11 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 if (!rc) rc = launch_pass_b(h, 0, 4 * cap, diag, 0, 0, false, m->rng_bnd2);
                 // their new positions decide what the neighbours get next step: pack it now and let exchange 1 travel while the
                 // main stream is still busy with the inner planes
+                if (!rc) rc = x1_plan(h);
                 if (!rc) rc = [&]() -> int {
                     LAUNCH(k_mg_classify_rng, cdiv(4 * cap, 256), 256, h->dp, h->cur, (const float4 *)h->alt.P, m->rng_bnd2, has_left ? 1 : 0, has_right ? 1 : 0,
-                           msg_view(h->msg_send[0], cap), msg_view(h->msg_send[1], cap), cap, h->d_err);
+                           msg_view(h->msg_send[0], h->x1_send_cap[0]), msg_view(h->msg_send[1], h->x1_send_cap[1]), h->x1_send_cap[0],
+                           h->x1_send_cap[1], h->d_err);
                     return SPHSM_OK;
                 }();
                 h->launch_stream = h->stream;
@@ -702,11 +763,16 @@ extern "C" int sphsm_step_group(sphsm_handle **hs, int nranks, int nsteps) {
                 if (coll[r] != coll[0] || count[r] != count[0]) return fail(hs[r], SPHSM_ERR_COMM, "ranks disagree on the phase program");
             }
             for (int r = 0; r < nranks; r++) CU(cudaStreamSynchronize(hs[r]->stream));
-            if (coll[0] == COLL_EXCH1) {
-                const size_t bytes = msg_bytes(h->send_cap);
+            if (coll[0] == COLL_EXCH1) {  // (message sizes as the NCCL step derives them: the two sides of a face must agree)
                 for (int r = 0; r < nranks; r++) {
-                    if (r > 0) CU(cudaMemcpy(hs[r]->msg_recv[0], hs[r - 1]->msg_send[1], bytes, cudaMemcpyDeviceToDevice));
-                    if (r < nranks - 1) CU(cudaMemcpy(hs[r]->msg_recv[1], hs[r + 1]->msg_send[0], bytes, cudaMemcpyDeviceToDevice));
+                    if (r > 0) {
+                        if (hs[r]->x1_recv_cap[0] != hs[r - 1]->x1_send_cap[1]) return fail(hs[r], SPHSM_ERR_COMM, "internal: the two sides of a slab face sized exchange 1 differently");
+                        CU(cudaMemcpy(hs[r]->msg_recv[0], hs[r - 1]->msg_send[1], msg_bytes(hs[r]->x1_recv_cap[0]), cudaMemcpyDeviceToDevice));
+                    }
+                    if (r < nranks - 1) {
+                        if (hs[r]->x1_recv_cap[1] != hs[r + 1]->x1_send_cap[0]) return fail(hs[r], SPHSM_ERR_COMM, "internal: the two sides of a slab face sized exchange 1 differently");
+                        CU(cudaMemcpy(hs[r]->msg_recv[1], hs[r + 1]->msg_send[0], msg_bytes(hs[r]->x1_recv_cap[1]), cudaMemcpyDeviceToDevice));
+                    }
                 }
             } else if (coll[0] == COLL_ALLREDUCE || coll[0] == COLL_ALLREDUCE_MOMENTS) {
                 const int c = count[0];

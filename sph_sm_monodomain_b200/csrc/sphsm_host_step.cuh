@@ -61,10 +61,13 @@ static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt, const int *n_dev 
     if (h->counts_ready) h->counts_ready = false;  // pass B filed keys, ranks and counts of these positions while it held them
     else LAUNCH(k_cell_count, cdiv(n, 256), 256, h->dp, h->cur.P, h->keys[0], h->keys[1], h->cell_count, n_dev, n_add);
     if (gt) gt->end_group(KG_HASH);
+    if (n_dev) trace_mark(h, "  cells counted");
     LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
     LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles, h->big_count);
     LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start);
+    if (n_dev) trace_mark(h, "  cell table scanned");
     LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0], h->skeys, n_dev, n_add);
+    if (n_dev) trace_mark(h, "  slots scattered");
     h->key_sorted = h->skeys;
     LAUNCH(k_cell_sort_ids, cdiv(h->dp.num_cells, 256), 256, h->cell_start, h->vals[0], h->cur.ID, h->dp.num_cells, h->big_cells, h->big_count);
     LAUNCH(k_cell_sort_big, 64, 256, h->cell_start, h->vals[0], h->vals[1], h->cur.ID, h->big_cells, h->big_count);

@@ -291,6 +291,12 @@ class Sim:
         keys = ("mode", "nranks", "rank", "n_local", "own_begin", "own_end", "halo_capacity", "slab_on")
         return dict(zip(keys, (int(v) for v in out)))
 
+    def x1_sizes(self):
+        """Capacities (particles) of the exchange-1 messages packed last: to left, to right, from left, from right."""
+        out = np.zeros(4, np.int32)
+        self._ck(self.lib.sphsm_comm_x1_sizes(self.h, _ip(out)))
+        return tuple(int(v) for v in out)
+
     def download_owned(self):
         """(ids, positions) of the particles this rank owns (all particles on a single GPU)."""
         cap = max(self.n, 1)

@@ -138,3 +138,56 @@ def test_slab_errors_are_reported():
     c.set_slab(0, slabs.num_planes(world, 0))
     grp.step(3)  # one rank, no neighbours: plain step through the phase program
     assert c.comm_info()["own_end"] - c.comm_info()["own_begin"] == len(pos)
+
+
+def test_exchange1_messages_follow_the_face_populations():
+    """Exchange-1 messages start at the full halo capacity, shrink to the lagged face population + margin after three unpacked
+    exchanges, are sized identically by the two sides of every face, go back to full capacity when the slab is set again, and leave every
+    bit of the result where the fixed-capacity messages put it."""
+    from sph_sm_monodomain_b200 import LocalGroup, Sim
+    from sph_sm_monodomain_b200.sim import tune
+
+    dims = (40, 9, 8)
+    pos, world, fixed, stim = setup_case(dims, 0.05)
+    n = len(pos)
+    npl = slabs.num_planes(world, 0)
+    parts = slabs.partition_planes(slabs.plane_histogram(pos, 0, npl), 3)
+
+    def run(dynamic):
+        tune("x1_dynamic", dynamic)
+        try:
+            sims = [make(Sim, pos, world, fixed, stim, True) for _ in range(3)]
+            grp = LocalGroup(sims)
+            for s, (lo, hi) in zip(sims, parts):
+                s.set_slab(lo, hi)
+            cap = sims[0].comm_info()["halo_capacity"]
+            sizes = []
+            for _ in range(8):
+                grp.step(1)
+                sizes.append([s.x1_sizes() for s in sims])
+            got, _ = grp.gather_positions(n)
+            # a new slab (collective) voids the history: full-size messages again
+            for s, (lo, hi) in zip(sims, parts):
+                s.set_slab(lo, hi)
+            grp.step(1)
+            after = [s.x1_sizes() for s in sims]
+            for s in sims:
+                s.close()
+            return cap, sizes, after, got
+        finally:
+            tune("x1_dynamic", 1)
+
+    cap, sizes, after, got = run(1)
+    assert all(v == cap for per in sizes[:3] for s in per for v in s), sizes[:3]
+    for per in sizes[3:]:
+        for r in range(3):
+            to_l, to_r, from_l, from_r = per[r]
+            if r > 0:
+                assert to_l < cap and from_l < cap and to_l % 256 == 0
+                assert from_l == per[r - 1][1] and to_l == per[r - 1][3]  # both sides of the face agree
+            if r < 2:
+                assert to_r < cap and from_r < cap
+    assert all(v == cap for s in after for v in s), after
+    cap0, sizes0, _, got0 = run(0)
+    assert cap0 == cap and all(v == cap for per in sizes0 for s in per for v in s)
+    assert got.tobytes() == got0.tobytes()

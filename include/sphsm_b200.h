@@ -233,9 +233,14 @@ int sphsm_comm_set_slab(sphsm_handle *h, int cell_lo, int cell_hi);
  *      [4] first owned slot [5] end of owned slots [6] halo message capacity [7] slab mode on */
 int sphsm_comm_info(sphsm_handle *h, int out8[8]);
 /* Exchange-1 message capacities (particles) of the exchange packed last: [0] to left [1] to right [2] from left [3] from right.
- * They follow the face populations of three exchanges earlier (a quarter + 2048 particles of margin, at most the halo capacity;
- * full capacity after every upload / new slab); sphsm_tune("x1_dynamic", 0) pins them to the halo capacity. */
+ * The halo capacity, unless sphsm_tune("x1_dynamic", 1) / SPHSM_X1_DYNAMIC=1 (every rank alike) lets the ncclSend / ncclRecv messages
+ * follow the face populations of three exchanges earlier (a quarter + 2048 particles of margin; full capacity after every upload /
+ * new slab): for particle sets whose face populations change smoothly — a regular lattice moves whole planes at once. */
 int sphsm_comm_x1_sizes(sphsm_handle *h, int out4[4]);
+/* 1 when exchange 1 of the NCCL mode runs as the push exchange: the packing kernel stores the halo / migrant records straight into
+ * the neighbour's receive slot (CUDA IPC mapping over NVLink) and a flag word publishes them; 0: ncclSend / ncclRecv (a neighbour
+ * could not be mapped, or some rank runs with SPHSM_P2P=0 — decided once, for all ranks, inside sphsm_comm_init). */
+int sphsm_comm_p2p(sphsm_handle *h);
 /* Compact read-back of the owned particles: original ids and positions (3 floats each); *count = owned particles. */
 int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int cap, int *count);
 /* Virtual ranks for testing the slab logic on ONE device: nranks handles (same device, capacity, world, slab_axis) form

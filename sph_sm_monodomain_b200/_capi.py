@@ -83,6 +83,7 @@ SYMBOLS = {
     "sphsm_comm_set_slab": (C.c_int, [_H, C.c_int, C.c_int]),
     "sphsm_comm_info": (C.c_int, [_H, _IP]),
     "sphsm_comm_x1_sizes": (C.c_int, [_H, _IP]),
+    "sphsm_comm_p2p": (C.c_int, [_H]),
     "sphsm_download_owned": (C.c_int, [_H, _IP, _FP, C.c_int, _IP]),
     "sphsm_comm_init_local": (C.c_int, [C.POINTER(_H), C.c_int]),
     "sphsm_step_group": (C.c_int, [C.POINTER(_H), C.c_int, C.c_int]),

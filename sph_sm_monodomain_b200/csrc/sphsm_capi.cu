@@ -54,8 +54,6 @@ struct sphsm_handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_meta = nullptr, ev_bnd = nullptr, ev_int = nullptr;
     bool moments_forked = false;
     bool allreduce_pending = false;        // slab step: the forked sums still need their allreduce (issued after exchange 1 on a shared communicator)
-    cudaEvent_t pev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // SPHSM_HOST_PROF: device-side brackets
-    double pacc[4] = {0, 0, 0, 0};
     double meta_wait_us = 0.0;             // SPHSM_HOST_PROF: host time spent waiting for the plane boundaries
     // NCCL mode: a rank-local step error (halo overflow, a particle crossing two planes) must not leave the peers waiting in
     // a collective.  It is recorded, rides as one extra element on the NEXT step's moment allreduce, and every rank returns the
@@ -127,6 +125,13 @@ struct sphsm_handle {
     int send_cap = 0;         // particles per exchange-1 message
     int alloc_n = 0;          // slots allocated per array (capacity + room for two halo messages in slab mode)
     uint8_t *msg_send[2] = {nullptr, nullptr}, *msg_recv[2] = {nullptr, nullptr};  // [0] left neighbour, [1] right neighbour
+    // push exchange (NCCL mode, neighbours reachable through CUDA IPC): exchange 1 is written by the packing kernel straight into the
+    // neighbour's receive slots over NVLink (p2p_push_view), a one-thread kernel publishes count + sequence number, the receiver's
+    // stream polls its own flag word (k_p2p_wait) — no ncclSend / ncclRecv, no host-known message size
+    uint8_t *p2p_block = nullptr;                   // [flags 256 B][from left, parity 0/1][from right, parity 0/1]
+    uint8_t *p2p_peer[2] = {nullptr, nullptr};      // the neighbours' blocks, mapped here
+    size_t p2p_slot_bytes = 0;
+    bool p2p_on = false;
     int *d_err = nullptr;
     // slot ranges of the slab (SlabMeta, sphsm_comm.cuh): two device copies written alternately by the sort of each step
     // (meta_cur = the one the latest sort wrote) and a ring of pinned host copies the host reads META_LAG steps late
@@ -187,9 +192,13 @@ static int g_pass_gen = getenv("SPHSM_PASS") ? atoi(getenv("SPHSM_PASS")) : 4;
 static int g_stage6 = getenv("SPHSM_STAGE6") ? atoi(getenv("SPHSM_STAGE6")) : 1;
 static int g_t6 = getenv("SPHSM_T6") ? atoi(getenv("SPHSM_T6")) : 128;
 static int g_b_step6 = getenv("SPHSM_B_STEP6") ? atoi(getenv("SPHSM_B_STEP6")) : 2;
-// 1: exchange-1 messages sized from the lagged face populations; 0: always the full halo capacity.  Process-wide: every rank of a group
-// must run with the same setting (the two sides of a face derive the message size from it)
-static int g_x1_dynamic = getenv("SPHSM_X1_DYNAMIC") ? atoi(getenv("SPHSM_X1_DYNAMIC")) : 1;
+// 1: ncclSend / ncclRecv exchange-1 messages sized from the lagged face populations; 0 (default): always the full halo capacity.
+// Process-wide: every rank of a group must run with the same setting (the two sides of a face derive the message size from it).
+// Off by default: a REGULAR lattice moves a whole lattice plane across a cell boundary in one step, which doubles a face
+// population at once (15625 -> 31250 on the 8M benchmark lattice; seen at 8 GPUs) — no margin short of the capacity covers that.
+// The push exchange below needs no size at all and is what the NCCL mode uses when the neighbours are reachable through CUDA IPC.
+static int g_x1_dynamic = getenv("SPHSM_X1_DYNAMIC") ? atoi(getenv("SPHSM_X1_DYNAMIC")) : 0;
+static int g_p2p = getenv("SPHSM_P2P") ? atoi(getenv("SPHSM_P2P")) : 1;  // 0: exchange 1 stays on ncclSend / ncclRecv (decided collectively at sphsm_comm_init)
 static int g_warp_path = getenv("SPHSM_WARP_PATH") ? atoi(getenv("SPHSM_WARP_PATH")) : 1;  // 0: small dense sets take the thread-per-particle kernels too
 extern "C" int sphsm_tune(const char *name, int value) {
     if (!name) return SPHSM_ERR_INVALID;
@@ -492,6 +501,12 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
     cudaFree(h->d_itmp);
     for (int k = 0; k < 2; k++) { cudaFree(h->msg_send[k]); cudaFree(h->msg_recv[k]); }
+    for (int k = 0; k < 2; k++)
+        if (h->p2p_peer[k]) cudaIpcCloseMemHandle(h->p2p_peer[k]);
+    // (the exported block itself is NOT freed while the push exchange was live: a neighbour may still have it mapped, and freeing
+    //  exported memory under an importer is undefined; destroy is not collective, so there is no safe point — ~13 MB per NCCL-mode
+    //  handle stay with the process until it exits)
+    if (h->p2p_block && !h->p2p_on) cudaFree(h->p2p_block);
     cudaFree(h->d_err); cudaFree(h->d_meta[0]); cudaFree(h->d_meta[1]); cudaFree(h->d_count);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     for (auto &e : h->ev_ring) if (e) cudaEventDestroy(e);

@@ -7,7 +7,9 @@
 //   k_mg_classify   stale halos are marked dead; owned particles whose NEW plane is the first / last owned plane or
 //                   beyond are copied into the message for that neighbour (halo refresh and migration are the same
 //                   message: the receiver's hash decides ownership) and stay here (as owned or as halo)
-//   exchange 1      messages with the count in the header, sized from the lagged face populations (x1_plan), ncclSend / ncclRecv
+//   exchange 1      messages with the count in the header.  NCCL mode with CUDA-IPC neighbours: the packing kernel stores them
+//                   straight into the neighbour's receive slot over NVLink and a flag word publishes them (push exchange, below);
+//                   otherwise ncclSend / ncclRecv of the full capacity (or of a lagged estimate, x1_plan)
 //   k_mg_unpack     arrivals are appended behind the local particles; unused message slots become dead entries that the
 //                   sort pushes into the limbo bucket
 //   ... hash, sort (canonical in-cell order = ascending original index, so both sides of a slab face hold that plane in
@@ -59,6 +61,49 @@ inline MsgView msg_view(uint8_t *base, int cap) {
     v.E = v.O + cap;
     v.ID = reinterpret_cast<int *>(v.E + cap);
     return v;
+}
+
+// ---- push exchange: the receive slots of a rank and the two words its neighbours publish into ---------------------------------
+// block = [flag from left, flag from right, pad to 256 B][slot(side 0, parity 0)][slot(0, 1)][slot(1, 0)][slot(1, 1)], a slot is one
+// message (header + arrays for the full halo capacity).  side 0 = written by the left neighbour, side 1 = by the right one.
+constexpr size_t P2P_FLAGS_BYTES = 256;
+inline size_t p2p_slot_bytes(int cap) { return (msg_bytes(cap) + 255) / 256 * 256; }
+inline size_t p2p_block_bytes(int cap) { return P2P_FLAGS_BYTES + 4 * p2p_slot_bytes(cap); }
+inline uint8_t *p2p_slot(uint8_t *block, int cap, int side, int parity) { return block + P2P_FLAGS_BYTES + (size_t)(side * 2 + parity) * p2p_slot_bytes(cap); }
+inline int *p2p_flag(uint8_t *block, int side) { return reinterpret_cast<int *>(block) + side; }
+
+// after the packing kernel (same stream): the counts go into the headers of the neighbours' slots, then — behind a system-scope
+// fence, so that whoever sees the sequence number also sees the counts and everything the packing kernel stored — the sequence
+// number of this exchange into their flag words
+__global__ void k_p2p_signal(const int *__restrict__ cntL, const int *__restrict__ cntR, int *hdrL, int *hdrR, int *flagL, int *flagR, int seq) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (hdrL) *reinterpret_cast<volatile int *>(hdrL) = *cntL;
+    if (hdrR) *reinterpret_cast<volatile int *>(hdrR) = *cntR;
+    __threadfence_system();
+    if (flagL) *reinterpret_cast<volatile int *>(flagL) = seq;
+    if (flagR) *reinterpret_cast<volatile int *>(flagR) = seq;
+}
+// before the unpack (same stream): lane `side` polls this rank's own flag word until the neighbour has published exchange `seq`.
+// A neighbour that never arrives (its process died, or the two sides lost count of the exchanges) ends the wait after
+// `timeout_ns` with err[1] raised, so the step fails like any other exchange error instead of hanging the device.
+__global__ void k_p2p_wait(const int *flagL, const int *flagR, int seq, int *err, unsigned long long timeout_ns) {
+    if (blockIdx.x != 0 || threadIdx.x > 1) return;
+    const int *f = threadIdx.x == 0 ? flagL : flagR;
+    if (!f) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+    while (*reinterpret_cast<const volatile int *>(f) - seq < 0) {
+        if ((++spins & 1023u) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) {
+                atomicAdd(&err[1], 1);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
 }
 
 // exchange 2 (pass A's records of a boundary plane) reuses the message buffers: [count, pad x3] [V x cap] [S x cap]

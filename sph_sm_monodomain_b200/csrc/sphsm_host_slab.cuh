@@ -81,6 +81,66 @@ static int comm_alloc(sphsm_handle *h) {
     return SPHSM_OK;
 }
 
+// ---- push exchange set-up: every rank maps its neighbours' receive blocks (CUDA IPC over NVLink); all ranks or none -------------
+// (collective: called by every rank from sphsm_comm_init, whatever its own outcome so far)
+static int p2p_setup(sphsm_handle *h) {
+    h->p2p_on = false;
+    if (h->nranks < 2) return SPHSM_OK;
+    const int cap = h->send_cap;
+    const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
+    int ok = g_p2p ? 1 : 0;
+    cudaIpcMemHandle_t hs[3];  // mine, the left neighbour's, the right neighbour's
+    memset(hs, 0, sizeof hs);
+    if (ok && cudaMalloc(&h->p2p_block, p2p_block_bytes(cap)) != cudaSuccess) { ok = 0; h->p2p_block = nullptr; }
+    if (ok) {
+        ok = cudaMemset(h->p2p_block, 0, p2p_block_bytes(cap)) == cudaSuccess && cudaMemset(h->p2p_block, 0xff, P2P_FLAGS_BYTES) == cudaSuccess &&  // flags = -1
+             cudaIpcGetMemHandle(&hs[0], h->p2p_block) == cudaSuccess;
+    }
+    cudaGetLastError();
+    uint8_t *d_hs = nullptr;
+    double *d_ok = nullptr;
+    CU(cudaMalloc(&d_hs, sizeof hs));
+    CU(cudaMalloc(&d_ok, sizeof(double)));
+    CU(cudaMemcpy(d_hs, hs, sizeof hs, cudaMemcpyHostToDevice));
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    NC(g_nccl.GroupStart());
+    if (has_left) {
+        NC(g_nccl.Send(d_hs, hb, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(d_hs + hb, hb, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
+    }
+    if (has_right) {
+        NC(g_nccl.Send(d_hs, hb, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(d_hs + 2 * hb, hb, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(hs, d_hs, sizeof hs, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 2 && ok; k++) {
+        if (!(k == 0 ? has_left : has_right)) continue;
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, hs[1 + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        else h->p2p_peer[k] = static_cast<uint8_t *>(ptr);
+    }
+    const double mine = ok ? 1.0 : 0.0;
+    double sum = 0.0;
+    CU(cudaMemcpy(d_ok, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(&sum, d_ok, sizeof sum, cudaMemcpyDeviceToHost));
+    cudaFree(d_hs);
+    cudaFree(d_ok);
+    if ((int)(sum + 0.5) == h->nranks) {
+        h->p2p_on = true;
+        h->p2p_slot_bytes = p2p_slot_bytes(cap);
+    } else {  // some rank could not map a neighbour (or runs with SPHSM_P2P=0): everybody stays on ncclSend / ncclRecv
+        for (int k = 0; k < 2; k++)
+            if (h->p2p_peer[k]) { cudaIpcCloseMemHandle(h->p2p_peer[k]); h->p2p_peer[k] = nullptr; }
+        if (h->p2p_block) { cudaFree(h->p2p_block); h->p2p_block = nullptr; }
+    }
+    return SPHSM_OK;
+}
+extern "C" int sphsm_comm_p2p(sphsm_handle *h) { return h && h->p2p_on ? 1 : 0; }
+
 extern "C" int sphsm_comm_unique_id(void *id128) {
     sphsm_handle *h = nullptr;
     if (!id128) return SPHSM_ERR_INVALID;
@@ -107,7 +167,8 @@ extern "C" int sphsm_comm_init(sphsm_handle *h, int nranks, int rank, const void
     // allreduce queued behind exchange 1 still ends before the sort does) and the two NCCL kernels then share the SMs.
     if (g_nccl.CommSplit && getenv("SPHSM_SPLIT_COMM")) NC(g_nccl.CommSplit(h->nccl_comm, 0, rank, &h->nccl_comm_red, nullptr));
     h->comm_mode = 1; h->nranks = nranks; h->rank = rank;
-    return comm_alloc(h);
+    if ((rc = comm_alloc(h)) != 0) return rc;
+    return p2p_setup(h);
 }
 
 extern "C" int sphsm_comm_init_local(sphsm_handle **hs, int nranks) {
@@ -286,7 +347,7 @@ static int x1_plan(sphsm_handle *h) {
     const int cap = h->send_cap;
     const long long q = h->x1_seq++, src = q - sphsm_handle::X1_LAG;
     for (int k = 0; k < 2; k++) h->x1_send_cap[k] = h->x1_recv_cap[k] = cap;
-    if (!g_x1_dynamic) return SPHSM_OK;
+    if (!g_x1_dynamic || h->p2p_on) return SPHSM_OK;  // (the push exchange moves the live entries only: nothing to size)
     // the newest exchange at least X1_LAG back that was unpacked (one voided by a mutator before its unpack left no record: on
     // every rank alike) and is still in the ring
     int slot = -1;
@@ -327,6 +388,37 @@ static int nccl_exchange1(sphsm_handle *h, cudaStream_t st) {
     NC(g_nccl.GroupEnd());
     return SPHSM_OK;
 }
+// ---- push exchange (p2p_on): where the packing kernels store, the publish, the wait ---------------------------------------------
+// message k (0: to the left neighbour, 1: to the right) of the exchange packed last: the arrays are the neighbour's receive slot
+// (my left neighbour receives it "from its right": side 1 of its block), the counter stays here (atomics)
+static MsgView x1_send_view(sphsm_handle *h, int k) {
+    if (!h->p2p_on || !h->p2p_peer[k]) return msg_view(h->msg_send[k], h->x1_send_cap[k]);
+    MsgView v = msg_view(p2p_slot(h->p2p_peer[k], h->send_cap, 1 - k, (int)((h->x1_seq - 1) & 1)), h->send_cap);
+    v.count = reinterpret_cast<int *>(h->msg_send[k]);
+    return v;
+}
+static MsgView x1_recv_view(sphsm_handle *h, int k) {
+    if (!h->p2p_on) return msg_view(h->msg_recv[k], h->x1_recv_cap[k]);
+    return msg_view(p2p_slot(h->p2p_block, h->send_cap, k, (int)((h->x1_seq - 1) & 1)), h->send_cap);
+}
+static int p2p_signal(sphsm_handle *h) {  // (on h->launch_stream, behind the packing kernel)
+    const int q = (int)(h->x1_seq - 1), par = q & 1, cap = h->send_cap;
+    const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
+    LAUNCH(k_p2p_signal, 1, 32, reinterpret_cast<const int *>(h->msg_send[0]), reinterpret_cast<const int *>(h->msg_send[1]),
+           has_left ? reinterpret_cast<int *>(p2p_slot(h->p2p_peer[0], cap, 1, par)) : nullptr,
+           has_right ? reinterpret_cast<int *>(p2p_slot(h->p2p_peer[1], cap, 0, par)) : nullptr,
+           has_left ? p2p_flag(h->p2p_peer[0], 1) : nullptr, has_right ? p2p_flag(h->p2p_peer[1], 0) : nullptr, q);
+    return SPHSM_OK;
+}
+static int p2p_wait(sphsm_handle *h) {  // (on h->launch_stream, before the unpack)
+    static const unsigned long long timeout_ns =
+        (unsigned long long)(getenv("SPHSM_P2P_TIMEOUT_S") ? std::max(1, atoi(getenv("SPHSM_P2P_TIMEOUT_S"))) : 60) * 1000000000ull;
+    const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
+    LAUNCH(k_p2p_wait, 1, 32, has_left ? p2p_flag(h->p2p_block, 0) : nullptr, has_right ? p2p_flag(h->p2p_block, 1) : nullptr, (int)(h->x1_seq - 1), h->d_err,
+           timeout_ns);
+    return SPHSM_OK;
+}
+
 // exchange 2: pass A's records of the two boundary planes, packed by k_mg_pack2 into the (free by now) message buffers.  The
 // messages have a fixed size like those of exchange 1 — the plane populations are only known on the device — and carry the
 // population in their header; the receiver (k_mg_unpack2) checks it against its own halo plane.
@@ -451,8 +543,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             CU(cudaMemsetAsync(h->msg_send[1], 0, 16, h->stream));
             if ((rc = x1_plan(h)) != 0) return rc;
             LAUNCH(k_mg_classify, cdiv(std::max(h->n_bound, 1), 256), 256, h->dp, h->cur, has_left ? 1 : 0, has_right ? 1 : 0,
-                   msg_view(h->msg_send[0], h->x1_send_cap[0]), msg_view(h->msg_send[1], h->x1_send_cap[1]), h->x1_send_cap[0], h->x1_send_cap[1],
-                   h->d_err, h->d_meta[h->meta_cur]);
+                   x1_send_view(h, 0), x1_send_view(h, 1), h->x1_send_cap[0], h->x1_send_cap[1], h->d_err, h->d_meta[h->meta_cur]);
             if (h->gt) h->gt->end_group(KG_OTHER);
             *coll = COLL_EXCH1;
             return SPHSM_OK;
@@ -462,11 +553,13 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
             const SlabMeta *prev = h->d_meta[h->meta_cur];
             {
                 const int slot = (int)((h->x1_seq - 1) % sphsm_handle::X1_RING);  // (its last read-back left X1_RING exchanges ago: a wait for form)
-                if (h->x1rec_seq[slot] >= 0) CU(cudaStreamWaitEvent(h->stream, h->ev_x1rec[slot], 0));
-                LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, prev, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, msg_view(h->msg_recv[0], h->x1_recv_cap[0]),
-                       msg_view(h->msg_recv[1], h->x1_recv_cap[1]), cap, h->x1_recv_cap[0], h->x1_recv_cap[1], h->d_err,
+                const bool record = g_x1_dynamic && !h->p2p_on;  // (only the sized ncclSend / ncclRecv messages need the populations on the host)
+                if (record && h->x1rec_seq[slot] >= 0) CU(cudaStreamWaitEvent(h->stream, h->ev_x1rec[slot], 0));
+                if (h->p2p_on && (rc = p2p_wait(h)) != 0) return rc;  // the neighbours have published this exchange
+                LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, prev, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, x1_recv_view(h, 0), x1_recv_view(h, 1), cap,
+                       h->x1_recv_cap[0], h->x1_recv_cap[1], h->d_err,
                        (const int *)h->msg_send[0], (const int *)h->msg_send[1], h->d_x1rec + 4 * slot);
-                if ((rc = x1_record_launch(h)) != 0) return rc;
+                if (record && (rc = x1_record_launch(h)) != 0) return rc;
             }
             // the entries to sort are the previous live slots + both message regions; the kernels read that count from `prev`,
             // the grids are sized for its upper bound.  (h->n itself is the host's last applied read-back: exact whenever the
@@ -555,11 +648,9 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 // check reads the buffer pass B is about to overwrite with the new positions — must have finished: ev_bnd is long past)
                 CU(cudaStreamWaitEvent(h->stream, h->ev_bnd, 0));
                 if ((rc = launch_pass_b(h, 0, h->own_bound, diag, 0, 0, false, m->rng_int2)) != 0) return rc;
-                if (g_host_prof_early() && h->pev[4]) CU(cudaEventRecord(h->pev[4], h->side_stream));
                 trace_mark(h, "pass B inner planes done");
                 rc = nccl_exchange2(h, h->side_stream);
                 trace_mark(h, "exchange 2 done", true);
-                if (g_host_prof_early() && h->pev[5]) CU(cudaEventRecord(h->pev[5], h->side_stream));
                 return rc;
             }
             if ((rc = launch_pass_a(h, 0, h->own_bound, 0, 0, m->rng_all)) != 0) return rc;
@@ -581,8 +672,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 if (!rc) rc = x1_plan(h);
                 if (!rc) rc = [&]() -> int {
                     LAUNCH(k_mg_classify_rng, cdiv(4 * cap, 256), 256, h->dp, h->cur, (const float4 *)h->alt.P, m->rng_bnd2, has_left ? 1 : 0, has_right ? 1 : 0,
-                           msg_view(h->msg_send[0], h->x1_send_cap[0]), msg_view(h->msg_send[1], h->x1_send_cap[1]), h->x1_send_cap[0],
-                           h->x1_send_cap[1], h->d_err);
+                           x1_send_view(h, 0), x1_send_view(h, 1), h->x1_send_cap[0], h->x1_send_cap[1], h->d_err);
                     return SPHSM_OK;
                 }();
                 h->launch_stream = h->stream;
@@ -663,7 +753,7 @@ static int mg_forked_allreduce(sphsm_handle *h) {
 }
 
 // SPHSM_HOST_PROF=1: host-side time of the slab step per phase (kernel launches / NCCL calls / the read-back wait), printed
-// by rank 0 every 64 steps — tells a launch-bound step from a device-bound one
+// by rank 0 every 64 steps — tells a launch-bound step from a device-bound one (the device side has its own tool: SPHSM_TRACE)
 static const bool g_host_prof = getenv("SPHSM_HOST_PROF") != nullptr;
 static double now_us() {
     timespec ts;
@@ -680,24 +770,20 @@ static int mg_step_nccl(sphsm_handle *h) {
         if ((rc = mg_phase(h, ph, &coll, &count)) != 0) return rc;
         const double t1 = g_host_prof ? now_us() : 0.0;
         if (coll == COLL_EXCH1) {
-            if (g_host_prof) {
-                for (int k = 0; k < 8; k++)
-                    if (!h->pev[k]) CU(cudaEventCreate(&h->pev[k]));
-                CU(cudaEventRecord(h->pev[0], h->stream));
-            }
-            rc = nccl_exchange1(h, h->stream);
-            if (g_host_prof) CU(cudaEventRecord(h->pev[1], h->stream));
-            if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[2], h->side_stream));
+            rc = h->p2p_on ? p2p_signal(h) : nccl_exchange1(h, h->stream);
             if (!rc && h->moments_forked && h->allreduce_pending) rc = mg_forked_allreduce(h);
             h->allreduce_pending = false;
-            if (g_host_prof && h->moments_forked) CU(cudaEventRecord(h->pev[3], h->side_stream));
         }
         else if (coll == COLL_EXCH1_TAKEN) {  // the exchange happened at the end of the previous step: only the allreduce is left
             if (h->moments_forked && h->allreduce_pending) rc = mg_forked_allreduce(h);
             h->allreduce_pending = false;
             if (!rc) rc = mg_check_interior(h);
         } else if (coll == COLL_EXCH1_EARLY) {  // next step's exchange 1, on the side stream behind the outer planes' pass B
-            rc = nccl_exchange1(h, h->side_stream);
+            if (h->p2p_on) {
+                h->launch_stream = h->side_stream;
+                rc = p2p_signal(h);
+                h->launch_stream = h->stream;
+            } else rc = nccl_exchange1(h, h->side_stream);
             if (!rc) CU(cudaEventRecord(h->ev_x1, h->side_stream));
             h->x1_early_pending = true;
             h->x1_early_valid = true;
@@ -716,20 +802,7 @@ static int mg_step_nccl(sphsm_handle *h) {
         return fail(h, SPHSM_ERR_COMM, h->local_error ? h->local_error_msg.c_str()
                                                       : "another rank of the slab group reported a step error (its sphsm_last_error has the cause)");
     }
-    if (g_host_prof && h->pev[5] && h->split) {  // device-side durations of the three collectives (this serialises the steps)
-        CU(cudaStreamSynchronize(h->stream));
-        CU(cudaStreamSynchronize(h->side_stream));
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->pev[0], h->pev[1]) == cudaSuccess) h->pacc[0] += ms * 1e3;
-        if (cudaEventElapsedTime(&ms, h->pev[2], h->pev[3]) == cudaSuccess) h->pacc[1] += ms * 1e3;
-        if (cudaEventElapsedTime(&ms, h->pev[4], h->pev[5]) == cudaSuccess) h->pacc[2] += ms * 1e3;
-        if (cudaEventElapsedTime(&ms, h->pev[0], h->pev[5]) == cudaSuccess) h->pacc[3] += ms * 1e3;
-        cudaGetLastError();
-    }
-    if (g_host_prof && ++steps_seen % 64 == 0) {
-        fprintf(stderr, "[sphsm dev prof rank %d, cumulative us over %d steps] exch1 %.0f allreduce+solve %.0f exch2+vn %.0f exch1-start..exch2-end %.0f\n",
-                h->rank, steps_seen, h->pacc[0], h->pacc[1], h->pacc[2], h->pacc[3]);
-    }
+    if (g_host_prof) steps_seen++;
     if (g_host_prof && steps_seen % 64 == 0 && h->rank == 0) {
         fprintf(stderr, "[sphsm host prof, us/step over %d steps] ", steps_seen);
         double tot = 0;

@@ -291,6 +291,10 @@ class Sim:
         keys = ("mode", "nranks", "rank", "n_local", "own_begin", "own_end", "halo_capacity", "slab_on")
         return dict(zip(keys, (int(v) for v in out)))
 
+    def push_exchange(self):
+        """True when exchange 1 runs as direct stores into the neighbours' memory (CUDA IPC over NVLink) instead of ncclSend / ncclRecv."""
+        return bool(self.lib.sphsm_comm_p2p(self.h))
+
     def x1_sizes(self):
         """Capacities (particles) of the exchange-1 messages packed last: to left, to right, from left, from right."""
         out = np.zeros(4, np.int32)

@@ -141,7 +141,7 @@ def test_slab_errors_are_reported():
 
 
 def test_exchange1_messages_follow_the_face_populations():
-    """Exchange-1 messages start at the full halo capacity, shrink to the lagged face population + margin after three unpacked
+    """sphsm_tune("x1_dynamic", 1): exchange-1 messages start at the full halo capacity, shrink to the lagged face population + margin after three unpacked
     exchanges, are sized identically by the two sides of every face, go back to full capacity when the slab is set again, and leave every
     bit of the result where the fixed-capacity messages put it."""
     from sph_sm_monodomain_b200 import LocalGroup, Sim
@@ -175,7 +175,7 @@ def test_exchange1_messages_follow_the_face_populations():
                 s.close()
             return cap, sizes, after, got
         finally:
-            tune("x1_dynamic", 1)
+            tune("x1_dynamic", 0)  # the default
 
     cap, sizes, after, got = run(1)
     assert all(v == cap for per in sizes[:3] for s in per for v in s), sizes[:3]

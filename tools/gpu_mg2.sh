@@ -11,4 +11,6 @@ for ln in sys.stdin:
     d=json.loads(ln); print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}, d['e2e']['value'], d['e2e']['h2d_bytes_per_step'], d.get('mg_parity'), d['roofline']['kernel_group_ms'])
 "
 tail -3 gpurun_out/bench_mg_$N.err
+# the sized ncclSend / ncclRecv messages (opt-in) on a jittered lattice
+SPHSM_P2P=0 SPHSM_X1_DYNAMIC=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 tools/mg_parity.py --steps 30 --quadratic --dims 128x20x20 2>/dev/null | grep "^{"
 SPHSM_HOST_PROF=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 128 --warmup 5 --no-cpu-baseline > gpurun_out/hostprof_$N.log 2>&1; grep "sphsm" gpurun_out/hostprof_$N.log | tail -4

@@ -69,6 +69,8 @@ struct sphsm_handle {
     uint32_t *key_sorted = nullptr;  // what the neighbour passes read: skeys, or the radix sort's sorted key buffer
     uint32_t *ghist = nullptr, *tile_state = nullptr, *tile_counter = nullptr;
     int sorted_buf = 0;  // which keys[] / vals[] hold the sorted result
+    bool order_inline = false;        // the last sort left the slots of a cell in arrival order: the gather applies the canonical order
+    const uint32_t *perm = nullptr;   // the permutation the last gather applied (slot -> source slot), for freeze_source
     uint32_t *cell_count = nullptr, *tile_sums = nullptr;  // counting sort: per-cell counts (kept zero between steps), scan scratch
     bool bounds_ready = false;                             // grid_sort already produced the cell_start table
     // CUDA graphs for small single-GPU steps (launch-latency bound): see graph_step
@@ -837,7 +839,7 @@ static FreezeSrc freeze_source(const sphsm_handle *h) {
     f.strict = h->prm.strict;
     f.sm = h->sm;
     f.prev_vel = h->prev_vel_valid ? h->alt.VEL : nullptr;
-    f.vals = h->vals[h->sorted_buf];
+    f.vals = h->perm;
     return f;
 }
 

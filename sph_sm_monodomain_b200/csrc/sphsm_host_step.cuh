@@ -64,14 +64,15 @@ static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt, const int *n_dev 
     if (n_dev) trace_mark(h, "  cells counted");
     LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
     LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles, h->big_count);
-    LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start);
+    LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start, h->big_cells, h->big_count);
     if (n_dev) trace_mark(h, "  cell table scanned");
     LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0], h->skeys, n_dev, n_add);
     if (n_dev) trace_mark(h, "  slots scattered");
     h->key_sorted = h->skeys;
-    LAUNCH(k_cell_sort_ids, cdiv(h->dp.num_cells, 256), 256, h->cell_start, h->vals[0], h->cur.ID, h->dp.num_cells, h->big_cells, h->big_count);
+    // cells of up to BIG_CELL entries get their canonical order inside the gather (grid_finish); the listed fuller ones here
     LAUNCH(k_cell_sort_big, 64, 256, h->cell_start, h->vals[0], h->vals[1], h->cur.ID, h->big_cells, h->big_count);
     h->sorted_buf = 0;
+    h->order_inline = true;
     h->bounds_ready = true;
     if (gt) gt->end_group(KG_SORT);
     return SPHSM_OK;
@@ -82,6 +83,7 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt, const int *n_dev = nullptr
     if (use_counting_sort(h) || n_dev) return grid_sort_counting(h, gt, n_dev, n_add, n_grid);  // (the slab step always sorts by counting)
     drop_counts(h);
     h->bounds_ready = false;
+    h->order_inline = false;
     const int passes = h->sort_passes;
     const int tiles = cdiv(n, SORT_TILE);
     if (!h->dry_run) {  // (a replayed graph carries its own copies of these nodes)
@@ -113,16 +115,19 @@ static int grid_sort(sphsm_handle *h, GroupTimer *gt, const int *n_dev = nullptr
 static int grid_finish(sphsm_handle *h, GroupTimer *gt, int fuse_goal, bool bounds_done = false, const int *n_dev = nullptr, int n_grid = -1) {
     const int n = n_grid >= 0 ? n_grid : h->n, src = h->sorted_buf;
     if (!bounds_done && !h->bounds_ready) LAUNCH(k_cell_bounds, cdiv(n + 1, 256), 256, h->keys[src], h->cell_start, n, h->dp.num_cells);
+    // counting sort: the gather applies the in-cell order itself and leaves the final permutation in the other index buffer
+    const int order_cells = h->order_inline ? h->dp.num_cells : 0;
+    h->perm = h->order_inline ? h->vals[src ^ 1] : h->vals[src];
     if (fuse_goal) {
-        if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev);
-        else LAUNCH(k_reorder_goal<false>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev);
+        if (fuse_goal == 2) LAUNCH(k_reorder_goal<true>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev, h->skeys, h->cell_start, order_cells, h->vals[src ^ 1]);
+        else LAUNCH(k_reorder_goal<false>, cdiv(n, 256), 256, h->dp, h->vals[src], h->cur, h->alt, h->sm, n_dev, h->skeys, h->cell_start, order_cells, h->vals[src ^ 1]);
         swap_sets(h, false);
         std::swap(h->cur.C, h->alt.C);
         std::swap(h->cur.GOAL, h->alt.GOAL);
         std::swap(h->cur.PV, h->alt.PV);
     } else {
         const bool all = h->prm.diagnostics || h->inter_live;
-        LAUNCH(k_reorder, cdiv(n, 256), 256, n, h->vals[src], h->cur, h->alt, all ? 1 : 0);
+        LAUNCH(k_reorder, cdiv(n, 256), 256, n, h->vals[src], h->cur, h->alt, all ? 1 : 0, h->skeys, h->cell_start, order_cells, h->vals[src ^ 1]);
         swap_sets(h, all);
     }
     if (gt) gt->end_group(KG_GRID);

@@ -12,6 +12,7 @@
 // m3Matrix.cpp:3-113, m3Matrix.h:288-318), m9Matrix::invert (Math3D/m9Matrix.cpp:10-102).
 #pragma once
 #include "sphsm_comm.cuh"
+#include "sphsm_sort.cuh"  // ordered_source (the gather applies the in-cell order)
 #include "sphsm_types.cuh"
 
 namespace sphsm {
@@ -475,10 +476,16 @@ __global__ void __launch_bounds__(256) k_goal_cvel(const __grid_constant__ DevPa
 // step from pass B's moment partials).  Saves the separate 48 B/particle re-read of k_goal_cvel.
 template <bool DIAG>
 __global__ void __launch_bounds__(256) k_reorder_goal(const __grid_constant__ DevParams p, const uint32_t *__restrict__ vals, Arrays src,
-                                                      Arrays dst, const SmState *__restrict__ sm, const int *__restrict__ n_dev) {
+                                                      Arrays dst, const SmState *__restrict__ sm, const int *__restrict__ n_dev,
+                                                      const uint32_t *__restrict__ skey, const int *__restrict__ cell_start, int order_cells,
+                                                      uint32_t *__restrict__ vals_out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= (n_dev ? *n_dev : p.n)) return;  // n_dev: the live count is still on its way to the host (slab step)
-    const uint32_t v = vals[s];
+    uint32_t v;
+    if (order_cells > 0) {  // counting sort: the cell's canonical order is applied here (ordered_source)
+        v = ordered_source(vals, skey, cell_start, src.ID, order_cells, s);
+        vals_out[s] = v;
+    } else v = vals[s];
     const float4 p4 = src.P[v], v4 = src.VEL[v], o4 = src.O[v], e4 = src.E[v];
     dst.P[s] = p4;
     // pass B writes VEL = (vel, dens) of every particle it integrates without reading it (the old velocity is not an input of

@@ -8,6 +8,8 @@
 //   k_reorder         gather the SoA state into the new slot order
 // Replaces Find_neighbors / Calculate_Cell_Position / Calculate_Cell_Hash, reference cpp:127-146, 199-213.
 #pragma once
+#include <limits.h>
+
 #include "sphsm_types.cuh"
 
 namespace sphsm {
@@ -343,9 +345,14 @@ __global__ void __launch_bounds__(1024) k_scan_tile_offsets(uint32_t *tile_sums,
         __syncthreads();
     }
 }
-// cell_start[c] = exclusive prefix of the counts for c in [0, m]; the count table is zeroed for the next step
+// In-cell order = ascending ORIGINAL index.  Cells of up to BIG_CELL particles (a lattice holds 1-8 per cell) are put in that order
+// by the gather itself (ordered_source); fuller cells (the reference's meshes reach 75) are listed here, while their counts pass
+// through, for k_cell_sort_big — the one-thread insertion sort of a 75-particle cell took 140 us of cfg2's 480 us step.
+constexpr int BIG_CELL = 8;
+// cell_start[c] = exclusive prefix of the counts for c in [0, m]; the count table is zeroed for the next step; cells (not the limbo
+// bucket m - 1) with more than BIG_CELL entries go on the worklist (big_count was cleared by k_scan_tile_offsets)
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restrict__ counts, int m, const uint32_t *__restrict__ tile_offsets,
-                                                             int *__restrict__ cell_start) {
+                                                             int *__restrict__ cell_start, int *__restrict__ big_cells, int *__restrict__ big_count) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
@@ -360,7 +367,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restric
     }
     uint32_t tsum = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_IPT; k++) tsum += c[k];
+    for (int k = 0; k < SCAN_IPT; k++) {
+        tsum += c[k];
+        if (c[k] > (uint32_t)BIG_CELL && base + k < m - 1) big_cells[atomicAdd(big_count, 1)] = base + k;
+    }
     uint32_t inc = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -406,35 +416,38 @@ __global__ void __launch_bounds__(256) k_cell_scatter(int n, const uint32_t *__r
     vals[slot] = (uint32_t)i;
     skey[slot] = key;
 }
-// in-cell order = ascending ORIGINAL index.  One thread per cell orders cells of up to BIG_CELL particles in place (a lattice
-// holds 1-8 per cell); fuller cells (the reference's meshes reach 75) go on a worklist for k_cell_sort_big — the one-thread
-// insertion sort of a 75-particle cell took 140 us of cfg2's 480 us step.
-constexpr int BIG_CELL = 8;
-__global__ void __launch_bounds__(256) k_cell_sort_ids(const int *__restrict__ cell_start, uint32_t *vals, const int *__restrict__ id_src, int num_cells,
-                                                       int *__restrict__ big_cells, int *__restrict__ big_count) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= num_cells) return;  // the limbo bucket (outside the grid / dead entries) has no order to keep
-    const int s = cell_start[c], e = cell_start[c + 1];
-    if (e - s < 2) return;
-    if (e - s == 2) {
-        const uint32_t v0 = vals[s], v1 = vals[s + 1];
-        if (id_src[v0] > id_src[v1]) { vals[s] = v1; vals[s + 1] = v0; }
-        return;
+// The source index that belongs in slot s once its cell is in canonical order: the member whose number of smaller original indices
+// equals the slot's position in the cell (indices are unique).  Evaluated by the gather for its own slot — the separate pass over
+// all cells (three dependent loads per cell, two launches) cost 21 us of the 306 us slab step at 8 GPUs and ~45 us at 8M on one —
+// from vals / ids that neighbouring threads of the same cell load as well (L1 hits).  Big cells were ordered in place before.
+__device__ __forceinline__ uint32_t ordered_source(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ skey, const int *__restrict__ cell_start,
+                                                   const int *__restrict__ id_src, int num_cells, int s) {
+    uint32_t v = vals[s];
+    const uint32_t key = skey[s];
+    if (key >= (uint32_t)num_cells) return v;  // the limbo bucket (outside the grid / dead entries) has no order to keep
+    const int cs = cell_start[key], cnt = cell_start[key + 1] - cs;
+    if (cnt < 2 || cnt > BIG_CELL) return v;
+    const int want = s - cs;
+    if (cnt == 2) {
+        const uint32_t u = vals[cs + 1 - want];  // the other member
+        const bool v_first = id_src[v] < id_src[u];
+        return (v_first == (want == 0)) ? v : u;  // in order already: keep; otherwise the two swap
     }
-    if (e - s > BIG_CELL) {
-        big_cells[atomicAdd(big_count, 1)] = c;
-        return;
+    uint32_t mv[BIG_CELL];
+    int mid[BIG_CELL];
+#pragma unroll
+    for (int k = 0; k < BIG_CELL; k++) {
+        mv[k] = k < cnt ? vals[cs + k] : 0u;
+        mid[k] = k < cnt ? id_src[mv[k]] : INT_MAX;
     }
-    for (int i = s + 1; i < e; i++) {
-        const uint32_t v = vals[i];
-        const int vid = id_src[v];
-        int j = i - 1;
-        while (j >= s && id_src[vals[j]] > vid) {
-            vals[j + 1] = vals[j];
-            j--;
-        }
-        vals[j + 1] = v;
+#pragma unroll
+    for (int a = 0; a < BIG_CELL; a++) {
+        int r = 0;
+#pragma unroll
+        for (int b = 0; b < BIG_CELL; b++) r += mid[b] < mid[a];
+        if (a < cnt && r == want) v = mv[a];
     }
+    return v;
 }
 // one warp per listed cell: every member's final position is the number of members with a smaller original index (indices are
 // unique); ranks go to `tmp` first so that no lane overwrites an entry another lane still has to read.  Resets the worklist.
@@ -457,14 +470,21 @@ __global__ void __launch_bounds__(256) k_cell_sort_big(const int *__restrict__ c
         __syncwarp();
     }
 }
-// (the worklist counter is cleared by the step's single-block scan kernel, before k_cell_sort_ids fills it again)
+// (the worklist counter is cleared by the step's single-block scan kernel, before k_scan_apply fills it again)
 
 // gather into the new slot order; `all` also permutes the intermediate / diagnostic arrays (after an upload, or
 // in diagnostics mode, they are live across a re-sort)
-__global__ void __launch_bounds__(256) k_reorder(int n, const uint32_t *__restrict__ vals, Arrays src, Arrays dst, int all) {
+// order_cells > 0: the slots of a cell are still in arrival order (counting sort); the canonical order is applied on the fly and the
+// final permutation goes to vals_out
+__global__ void __launch_bounds__(256) k_reorder(int n, const uint32_t *__restrict__ vals, Arrays src, Arrays dst, int all, const uint32_t *__restrict__ skey,
+                                                 const int *__restrict__ cell_start, int order_cells, uint32_t *__restrict__ vals_out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    uint32_t v = vals[s];
+    uint32_t v;
+    if (order_cells > 0) {
+        v = ordered_source(vals, skey, cell_start, src.ID, order_cells, s);
+        vals_out[s] = v;
+    } else v = vals[s];
     const float4 p4 = src.P[v], e4 = src.E[v];
     dst.P[s] = p4;
     dst.VEL[s] = src.VEL[v];

@@ -71,7 +71,9 @@ struct sphsm_handle {
     int sorted_buf = 0;  // which keys[] / vals[] hold the sorted result
     bool order_inline = false;        // the last sort left the slots of a cell in arrival order: the gather applies the canonical order
     const uint32_t *perm = nullptr;   // the permutation the last gather applied (slot -> source slot), for freeze_source
-    uint32_t *cell_count = nullptr, *tile_sums = nullptr;  // counting sort: per-cell counts (kept zero between steps), scan scratch
+    uint32_t *cell_count = nullptr;               // counting sort: per-cell counts (kept zero between steps)
+    unsigned long long *scan_state = nullptr;     // single-pass scan: one published word per tile (k_scan_onepass)
+    uint32_t *scan_ctl = nullptr;                 //   ticket, blocks done, epoch (+ pad)
     bool bounds_ready = false;                             // grid_sort already produced the cell_start table
     // CUDA graphs for small single-GPU steps (launch-latency bound): see graph_step
     bool dry_run = false;  // replaying a captured step: the host-side state transitions run, launches and stream calls do not
@@ -371,12 +373,19 @@ static int setup_grid_buffers(sphsm_handle *h) {
     h->cell_start = nullptr;
     CU(cudaMalloc(&h->cell_start, ((size_t)h->dp.num_cells + 2) * sizeof(int)));
     if (h->cell_count) cudaFree(h->cell_count);
-    if (h->tile_sums) cudaFree(h->tile_sums);
-    h->cell_count = h->tile_sums = nullptr;
+    if (h->scan_state) cudaFree(h->scan_state);
+    h->cell_count = nullptr;
+    h->scan_state = nullptr;
     CU(cudaMalloc(&h->cell_count, ((size_t)h->dp.num_cells + 2 + SCAN_IPT) * sizeof(uint32_t)));
     CU(cudaMemset(h->cell_count, 0, ((size_t)h->dp.num_cells + 2 + SCAN_IPT) * sizeof(uint32_t)));
     h->counts_ready = false;
-    CU(cudaMalloc(&h->tile_sums, ((size_t)(h->dp.num_cells + 2) / SCAN_TILE + 2) * sizeof(uint32_t)));
+    {
+        const size_t tiles = (size_t)(h->dp.num_cells + 2) / SCAN_TILE + 2;
+        CU(cudaMalloc(&h->scan_state, tiles * sizeof(unsigned long long)));
+        CU(cudaMemset(h->scan_state, 0, tiles * sizeof(unsigned long long)));
+        if (!h->scan_ctl) CU(cudaMalloc(&h->scan_ctl, 4 * sizeof(uint32_t)));
+        CU(cudaMemset(h->scan_ctl, 0, 4 * sizeof(uint32_t)));  // epoch 0 again: matches the zeroed state words (status 0 = nothing published)
+    }
     int bits = 1;
     while ((1ll << bits) < (long long)h->dp.num_cells + 1) bits++;
     h->sort_passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
@@ -468,8 +477,8 @@ static int create_impl(const sphsm_params *p, sphsm_handle **out, sphsm_handle *
     CU(cudaMalloc(&h->tile_counter, MAX_SORT_PASSES * sizeof(uint32_t)));
     CU(cudaMalloc(&h->slot_of, (size_t)cap * sizeof(int)));
     CU(cudaMalloc(&h->big_cells, ((size_t)cap / BIG_CELL + 2) * sizeof(int)));
-    CU(cudaMalloc(&h->big_count, sizeof(int)));
-    CU(cudaMemset(h->big_count, 0, sizeof(int)));
+    CU(cudaMalloc(&h->big_count, 2 * sizeof(int)));  // (one per scan epoch parity)
+    CU(cudaMemset(h->big_count, 0, 2 * sizeof(int)));
     CU(cudaMalloc(&h->d_dp, sizeof(DevParams)));
     CU(cudaMalloc(&h->sm, sizeof(SmState)));
     CU(cudaMemset(h->sm, 0, sizeof(SmState)));
@@ -498,7 +507,7 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     free_arrays(h->alt, false);
     for (int k = 0; k < 2; k++) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
     cudaFree(h->skeys);
-    cudaFree(h->cell_count); cudaFree(h->tile_sums); cudaFree(h->big_cells); cudaFree(h->big_count);
+    cudaFree(h->cell_count); cudaFree(h->scan_state); cudaFree(h->scan_ctl); cudaFree(h->big_cells); cudaFree(h->big_count);
     cudaFree(h->ghist); cudaFree(h->tile_state); cudaFree(h->tile_counter); cudaFree(h->cell_start); cudaFree(h->slot_of);
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
     cudaFree(h->d_itmp);

@@ -62,15 +62,13 @@ static int grid_sort_counting(sphsm_handle *h, GroupTimer *gt, const int *n_dev 
     else LAUNCH(k_cell_count, cdiv(n, 256), 256, h->dp, h->cur.P, h->keys[0], h->keys[1], h->cell_count, n_dev, n_add);
     if (gt) gt->end_group(KG_HASH);
     if (n_dev) trace_mark(h, "  cells counted");
-    LAUNCH(k_scan_tile_sums, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums);
-    LAUNCH(k_scan_tile_offsets, 1, 1024, h->tile_sums, tiles, h->big_count);
-    LAUNCH(k_scan_apply, tiles, SCAN_THREADS, h->cell_count, m, h->tile_sums, h->cell_start, h->big_cells, h->big_count);
+    LAUNCH(k_scan_onepass, tiles, SCAN_THREADS, h->cell_count, m, h->cell_start, h->scan_state, h->scan_ctl, h->big_cells, h->big_count);
     if (n_dev) trace_mark(h, "  cell table scanned");
     LAUNCH(k_cell_scatter, cdiv(n, 256), 256, n, h->keys[0], h->keys[1], h->cell_start, h->vals[0], h->skeys, n_dev, n_add);
     if (n_dev) trace_mark(h, "  slots scattered");
     h->key_sorted = h->skeys;
     // cells of up to BIG_CELL entries get their canonical order inside the gather (grid_finish); the listed fuller ones here
-    LAUNCH(k_cell_sort_big, 64, 256, h->cell_start, h->vals[0], h->vals[1], h->cur.ID, h->big_cells, h->big_count);
+    LAUNCH(k_cell_sort_big, 64, 256, h->cell_start, h->vals[0], h->vals[1], h->cur.ID, h->big_cells, h->big_count, h->scan_ctl);
     h->sorted_buf = 0;
     h->order_inline = true;
     h->bounds_ready = true;
@@ -493,7 +491,7 @@ static std::string step_signature(const sphsm_handle *h) {
     put(&h->alt, sizeof(Arrays));
     put(&h->dp, sizeof(DevParams));
     put(&h->prm, sizeof(sphsm_params));
-    const void *ptrs[] = {h->cell_start, h->cell_count, h->tile_sums, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->big_cells, h->big_count,
+    const void *ptrs[] = {h->cell_start, h->cell_count, h->scan_state, h->scan_ctl, h->keys[0], h->keys[1], h->vals[0], h->vals[1], h->big_cells, h->big_count,
                           h->sm, h->partial, h->totals, h->d_dp, h->ghist, h->tile_state, h->tile_counter, h->scratch, h->skeys};
     put(ptrs, sizeof(ptrs));
     const int flags[] = {h->counts_ready, h->bounds_ready, h->sorted_buf, g_pass_gen, h->red_blocks, h->sort_passes, (int)h->grid_valid, (int)warp_path(h), g_stage6, g_t6, g_b_step6};

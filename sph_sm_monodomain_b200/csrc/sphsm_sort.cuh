@@ -5,6 +5,10 @@
 //                     shared memory so the scatter leaves the SM as coalesced runs
 //   k_cell_order_fix  (strict mode) in-cell order = ascending ORIGINAL index, the reference's bucket order
 //   k_cell_bounds     cell_start table (num_cells + 2 entries, prefix form: cell c = [start[c], start[c+1]))
+//   k_cell_count / k_scan_onepass / k_cell_scatter / k_cell_sort_big
+//                     the counting sort of the fast path: per-cell counts + provisional ranks (filed by pass B on one GPU), cell table
+//                     by a single-pass scan, slots; in-cell order (ascending original index) is applied by the gather itself
+//                     (ordered_source), cells of more than 8 entries by a warp each
 //   k_reorder         gather the SoA state into the new slot order
 // Replaces Find_neighbors / Calculate_Cell_Position / Calculate_Cell_Hash, reference cpp:127-146, 199-213.
 #pragma once
@@ -287,77 +291,49 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_IPT = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_IPT;
 
-// sum of each tile of the count table
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t *__restrict__ in, int m, uint32_t *__restrict__ tile_sums) {
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
-    uint32_t v = 0;
-    if (base + SCAN_IPT <= m) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(in + base), b = *reinterpret_cast<const uint4 *>(in + base + 4);
-        v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-    } else {
-        for (int k = 0; k < SCAN_IPT; k++)
-            if (base + k < m) v += in[base + k];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < SCAN_THREADS / 32; w++) t += s_warp[w];
-        tile_sums[blockIdx.x] = t;
-    }
-}
-// exclusive scan of the tile sums in place (one block; chunks of 1024 with a running carry)
-__global__ void __launch_bounds__(1024) k_scan_tile_offsets(uint32_t *tile_sums, int nb, int *clear_me) {
-    if (threadIdx.x == 0 && clear_me) *clear_me = 0;
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < nb; base += 1024) {
-        const int idx = base + threadIdx.x;
-        const uint32_t v = idx < nb ? tile_sums[idx] : 0u;
-        uint32_t inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = s_warp[lane], winc = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
-                if (lane >= o) winc += t;
-            }
-            s_warp[lane] = winc - w;  // exclusive warp bases
-        }
-        __syncthreads();
-        const uint32_t carry = s_carry;
-        if (idx < nb) tile_sums[idx] = carry + s_warp[warp] + inc - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + inc;
-        __syncthreads();
-    }
-}
 // In-cell order = ascending ORIGINAL index.  Cells of up to BIG_CELL particles (a lattice holds 1-8 per cell) are put in that order
-// by the gather itself (ordered_source); fuller cells (the reference's meshes reach 75) are listed here, while their counts pass
+// by the gather itself (ordered_source); fuller cells (the reference's meshes reach 75) are listed by the scan, while their counts pass
 // through, for k_cell_sort_big — the one-thread insertion sort of a 75-particle cell took 140 us of cfg2's 480 us step.
 constexpr int BIG_CELL = 8;
-// cell_start[c] = exclusive prefix of the counts for c in [0, m]; the count table is zeroed for the next step; cells (not the limbo
-// bucket m - 1) with more than BIG_CELL entries go on the worklist (big_count was cleared by k_scan_tile_offsets)
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restrict__ counts, int m, const uint32_t *__restrict__ tile_offsets,
-                                                             int *__restrict__ cell_start, int *__restrict__ big_cells, int *__restrict__ big_count) {
+// skey[slot] = the key again, in slot order (the in-cell ordering below permutes slots of ONE cell, so it stays valid): the
+// neighbour passes read it instead of recomputing cell coordinates
+__global__ void __launch_bounds__(256) k_cell_scatter(int n, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
+                                                      const int *__restrict__ cell_start, uint32_t *__restrict__ vals, uint32_t *__restrict__ skey,
+                                                      const int *__restrict__ n_dev, int n_add) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n_dev ? *n_dev + n_add : n)) return;
+    const uint32_t key = keys[i], slot = (uint32_t)cell_start[key] + rank[i];
+    vals[slot] = (uint32_t)i;
+    skey[slot] = key;
+}
+// cell_start[c] = exclusive prefix of the counts for c in [0, m], in ONE pass (decoupled look-back; rounds 1-2 ran tile sums / a
+// single-block scan of them / apply as three launches: 16 us of the slab step at 8 GPUs): a block takes the next tile by ticket,
+// publishes its tile sum, looks back over its predecessors' published sums / inclusive prefixes (a warp reads 32 of them at a time)
+// and writes its slice of cell_start; the count table is zeroed for the next step; cells (not the limbo bucket m - 1) with more
+// than BIG_CELL entries go on the worklist.  The published words carry the epoch of the launch — ctl[2], advanced by the last block to finish, which also rewinds
+// the ticket — so nothing has to be cleared between launches and a captured graph can replay the kernel with frozen arguments.
+//   ctl[0] ticket, ctl[1] blocks done, ctl[2] epoch;  state[tile] = epoch << 34 | status << 32 | value  (status 1: tile sum, 2: inclusive prefix)
+//   big_count[2]: the worklist counter of this launch is big_count[epoch & 1]; the other one is cleared for the next launch
+__device__ __forceinline__ unsigned long long scan_word(uint32_t epoch, uint32_t status, uint32_t value) {
+    return ((unsigned long long)(epoch & 0x3fffffffu) << 34) | ((unsigned long long)status << 32) | value;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(uint32_t *__restrict__ counts, int m, int *__restrict__ cell_start,
+                                                               unsigned long long *state, uint32_t *ctl, int *__restrict__ big_cells, int *big_count) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_tile, s_epoch, s_prefix;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+    if (threadIdx.x == 0) {
+        s_epoch = *reinterpret_cast<volatile uint32_t *>(ctl + 2);
+        s_tile = atomicAdd(ctl, 1u);
+    }
+    __syncthreads();
+    const uint32_t epoch = s_epoch & 0x3fffffffu;
+    const int tile = (int)s_tile;
+    int *my_big = big_count + (epoch & 1u);
+    if (tile == 0 && threadIdx.x == 0) big_count[(epoch + 1u) & 1u] = 0;
+    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_IPT;
     uint32_t c[SCAN_IPT];
-    const bool full = base + SCAN_IPT <= m;  // 32 contiguous bytes per thread: two 16-byte accesses each way
+    const bool full = base + SCAN_IPT <= m;
     if (full) {
         const uint4 a = *reinterpret_cast<const uint4 *>(counts + base), b = *reinterpret_cast<const uint4 *>(counts + base + 4);
         c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
@@ -369,7 +345,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restric
 #pragma unroll
     for (int k = 0; k < SCAN_IPT; k++) {
         tsum += c[k];
-        if (c[k] > (uint32_t)BIG_CELL && base + k < m - 1) big_cells[atomicAdd(big_count, 1)] = base + k;
+        if (c[k] > (uint32_t)BIG_CELL && base + k < m - 1) big_cells[atomicAdd(my_big, 1)] = base + k;
     }
     uint32_t inc = tsum;
 #pragma unroll
@@ -379,11 +355,45 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restric
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
+    if (warp == 0) {
+        uint32_t total = lane < SCAN_THREADS / 32 ? s_warp[lane] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        uint32_t prefix = 0;
+        if (tile > 0) {
+            if (lane == 0) atomicExch(state + tile, scan_word(epoch, 1u, total));
+            int j = tile - 1;
+            unsigned spins = 0;
+            while (true) {
+                const int idx = j - lane;
+                unsigned long long w = scan_word(epoch, 2u, 0u);  // (before tile 0: an inclusive prefix of nothing)
+                bool ready;
+                do {
+                    if (idx >= 0) w = *reinterpret_cast<volatile unsigned long long *>(state + idx);
+                    ready = (uint32_t)(w >> 34) == epoch && ((w >> 32) & 3u) != 0u;
+                } while (__any_sync(0xffffffffu, !ready) && ++spins < (1u << 26));  // (the bound only guards against a hang: never reached)
+                const uint32_t val = (uint32_t)w;
+                const unsigned done = __ballot_sync(0xffffffffu, ((w >> 32) & 3u) == 2u);
+                const int first = done ? __ffs(done) - 1 : 31;  // nearest predecessor that already holds an inclusive prefix
+                uint32_t part = lane <= first ? val : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                prefix += part;
+                if (done || spins >= (1u << 26)) break;
+                j -= 32;
+            }
+        }
+        if (lane == 0) {
+            atomicExch(state + tile, scan_word(epoch, 2u, prefix + total));
+            s_prefix = prefix;
+        }
+    }
+    __syncthreads();
     uint32_t wbase = 0;
 #pragma unroll
     for (int w = 0; w < SCAN_THREADS / 32; w++)
         if (w < warp) wbase += s_warp[w];
-    uint32_t run = tile_offsets[blockIdx.x] + wbase + inc - tsum;
+    uint32_t run = s_prefix + wbase + inc - tsum;
     if (full) {
         int o[SCAN_IPT];
 #pragma unroll
@@ -404,18 +414,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t *__restric
             run += c[k];
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ctl + 1, 1u) == gridDim.x - 1) {  // the last block: rewind for the next launch
+            ctl[0] = 0u;
+            ctl[1] = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t *>(ctl + 2) = s_epoch + 1u;
+        }
+    }
 }
-// skey[slot] = the key again, in slot order (the in-cell ordering below permutes slots of ONE cell, so it stays valid): the
-// neighbour passes read it instead of recomputing cell coordinates
-__global__ void __launch_bounds__(256) k_cell_scatter(int n, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ rank,
-                                                      const int *__restrict__ cell_start, uint32_t *__restrict__ vals, uint32_t *__restrict__ skey,
-                                                      const int *__restrict__ n_dev, int n_add) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (n_dev ? *n_dev + n_add : n)) return;
-    const uint32_t key = keys[i], slot = (uint32_t)cell_start[key] + rank[i];
-    vals[slot] = (uint32_t)i;
-    skey[slot] = key;
-}
+
 // The source index that belongs in slot s once its cell is in canonical order: the member whose number of smaller original indices
 // equals the slot's position in the cell (indices are unique).  Evaluated by the gather for its own slot — the separate pass over
 // all cells (three dependent loads per cell, two launches) cost 21 us of the 306 us slab step at 8 GPUs and ~45 us at 8M on one —
@@ -450,11 +460,11 @@ __device__ __forceinline__ uint32_t ordered_source(const uint32_t *__restrict__ 
     return v;
 }
 // one warp per listed cell: every member's final position is the number of members with a smaller original index (indices are
-// unique); ranks go to `tmp` first so that no lane overwrites an entry another lane still has to read.  Resets the worklist.
+// unique); ranks go to `tmp` first so that no lane overwrites an entry another lane still has to read.
 __global__ void __launch_bounds__(256) k_cell_sort_big(const int *__restrict__ cell_start, uint32_t *vals, uint32_t *tmp, const int *__restrict__ id_src,
-                                                       const int *__restrict__ big_cells, int *big_count) {
+                                                       const int *__restrict__ big_cells, const int *__restrict__ big_count, const uint32_t *__restrict__ ctl) {
     const int lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int total = *big_count;
+    const int total = big_count[(ctl[2] - 1u) & 1u];  // the counter of the scan launch that has just finished (it advanced the epoch)
     for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < total; k += nwarps) {
         const int c = big_cells[k];
         const int s = cell_start[c], e = cell_start[c + 1];
@@ -470,7 +480,7 @@ __global__ void __launch_bounds__(256) k_cell_sort_big(const int *__restrict__ c
         __syncwarp();
     }
 }
-// (the worklist counter is cleared by the step's single-block scan kernel, before k_scan_apply fills it again)
+// (the other worklist counter is cleared by the scan kernel of the same step, for the next one)
 
 // gather into the new slot order; `all` also permutes the intermediate / diagnostic arrays (after an upload, or
 // in diagnostics mode, they are live across a re-sort)

@@ -519,10 +519,12 @@ def run_ours(args, wl, rank, world_size, local_rank):
                        + " to pinned host memory; copies overlap the next step on the library's copy streams, the timed region "
                          "ends when the last result is in host memory (sphsm_sync); bytes summed over ranks"}
     assert np.isfinite(pos_host.numpy()[:n_read]).all()
-    push_exchange = None
+    push_exchange = push_allreduce = None
     if world_size > 1:
         push_exchange = ("push: the packing kernel stores into the neighbour's receive slot (CUDA IPC over NVLink), flag word + polling kernel"
                          if sim.push_exchange() else "ncclSend / ncclRecv of full-capacity messages")
+        push_allreduce = ("push: one kernel stores the rank's sums into every rank's landing area (CUDA IPC over NVLink), waits for the others' and adds in rank order"
+                          if sim.push_allreduce() else "ncclAllReduce")
 
     also = None
     if rank == 0 and world_size == 1 and wl["key"] == "8m" and not args.no_also:
@@ -546,6 +548,7 @@ def run_ours(args, wl, rank, world_size, local_rank):
                 "roofline": roofline}
         if world_size > 1:
             line["config"]["exchange1"] = push_exchange
+            line["config"]["moment_allreduce"] = push_allreduce
         if pacing:
             line["config"]["pacing"] = {"stimulate_every": pacing[0], "turn_off_after": pacing[1], "inside_timed_region": True}
         if mg_parity is not None:

@@ -237,9 +237,11 @@ int sphsm_comm_info(sphsm_handle *h, int out8[8]);
  * follow the face populations of three exchanges earlier (a quarter + 2048 particles of margin; full capacity after every upload /
  * new slab): for particle sets whose face populations change smoothly — a regular lattice moves whole planes at once. */
 int sphsm_comm_x1_sizes(sphsm_handle *h, int out4[4]);
-/* 1 when exchange 1 of the NCCL mode runs as the push exchange: the packing kernel stores the halo / migrant records straight into
- * the neighbour's receive slot (CUDA IPC mapping over NVLink) and a flag word publishes them; 0: ncclSend / ncclRecv (a neighbour
- * could not be mapped, or some rank runs with SPHSM_P2P=0 — decided once, for all ranks, inside sphsm_comm_init). */
+/* Bit 0: exchange 1 of the NCCL mode runs as the push exchange — the packing kernel stores the halo / migrant records straight into
+ * the neighbour's receive slot (CUDA IPC mapping over NVLink) and a flag word publishes them.  Bit 1: the small allreduces of the
+ * step (moment sums + error flag) run as the push allreduce — one kernel stores the rank's values into every rank's landing area,
+ * waits for the others' and adds them in rank order.  0: ncclSend / ncclRecv / ncclAllReduce (a peer could not be mapped, more than
+ * 32 ranks, or some rank runs with SPHSM_P2P=0 / SPHSM_P2P_RED=0 — decided once, for all ranks, inside sphsm_comm_init). */
 int sphsm_comm_p2p(sphsm_handle *h);
 /* Compact read-back of the owned particles: original ids and positions (3 floats each); *count = owned particles. */
 int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int cap, int *count);

@@ -133,9 +133,12 @@ struct sphsm_handle {
     // neighbour's receive slots over NVLink (p2p_push_view), a one-thread kernel publishes count + sequence number, the receiver's
     // stream polls its own flag word (k_p2p_wait) — no ncclSend / ncclRecv, no host-known message size
     uint8_t *p2p_block = nullptr;                   // [flags 256 B][from left, parity 0/1][from right, parity 0/1]
-    uint8_t *p2p_peer[2] = {nullptr, nullptr};      // the neighbours' blocks, mapped here
+    uint8_t *p2p_peer[2] = {nullptr, nullptr};      // the neighbours' blocks, mapped here (entries of p2p_all)
+    std::vector<uint8_t *> p2p_all;                 // every rank's block (own = p2p_block): the push allreduce stores into all of them
+    uint8_t **d_p2p_all = nullptr;                  //   the same table in device memory
     size_t p2p_slot_bytes = 0;
-    bool p2p_on = false;
+    bool p2p_on = false, p2p_red_on = false;        // push exchange / push allreduce live (decided collectively in sphsm_comm_init)
+    long long red_seq = 0;                          // push allreduces issued so far
     int *d_err = nullptr;
     // slot ranges of the slab (SlabMeta, sphsm_comm.cuh): two device copies written alternately by the sort of each step
     // (meta_cur = the one the latest sort wrote) and a ring of pinned host copies the host reads META_LAG steps late
@@ -202,6 +205,7 @@ static int g_b_step6 = getenv("SPHSM_B_STEP6") ? atoi(getenv("SPHSM_B_STEP6")) :
 // population at once (15625 -> 31250 on the 8M benchmark lattice; seen at 8 GPUs) — no margin short of the capacity covers that.
 // The push exchange below needs no size at all and is what the NCCL mode uses when the neighbours are reachable through CUDA IPC.
 static int g_x1_dynamic = getenv("SPHSM_X1_DYNAMIC") ? atoi(getenv("SPHSM_X1_DYNAMIC")) : 0;
+static int g_p2p_red = getenv("SPHSM_P2P_RED") ? atoi(getenv("SPHSM_P2P_RED")) : 1;  // 0: the allreduces stay on ncclAllReduce (collective decision, like SPHSM_P2P)
 static int g_p2p = getenv("SPHSM_P2P") ? atoi(getenv("SPHSM_P2P")) : 1;  // 0: exchange 1 stays on ncclSend / ncclRecv (decided collectively at sphsm_comm_init)
 static int g_warp_path = getenv("SPHSM_WARP_PATH") ? atoi(getenv("SPHSM_WARP_PATH")) : 1;  // 0: small dense sets take the thread-per-particle kernels too
 extern "C" int sphsm_tune(const char *name, int value) {
@@ -512,8 +516,9 @@ extern "C" int sphsm_destroy(sphsm_handle *h) {
     cudaFree(h->d_dp); cudaFree(h->sm); cudaFree(h->partial); cudaFree(h->totals); cudaFree(h->scratch); cudaFree(h->d_aos); cudaFree(h->d_tmp);
     cudaFree(h->d_itmp);
     for (int k = 0; k < 2; k++) { cudaFree(h->msg_send[k]); cudaFree(h->msg_recv[k]); }
-    for (int k = 0; k < 2; k++)
-        if (h->p2p_peer[k]) cudaIpcCloseMemHandle(h->p2p_peer[k]);
+    for (size_t k = 0; k < h->p2p_all.size(); k++)
+        if (h->p2p_all[k] && h->p2p_all[k] != h->p2p_block) cudaIpcCloseMemHandle(h->p2p_all[k]);
+    if (h->d_p2p_all) cudaFree(h->d_p2p_all);
     // (the exported block itself is NOT freed while the push exchange was live: a neighbour may still have it mapped, and freeing
     //  exported memory under an importer is undefined; destroy is not collective, so there is no safe point — ~13 MB per NCCL-mode
     //  handle stay with the process until it exits)

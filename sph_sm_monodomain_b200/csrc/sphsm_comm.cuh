@@ -66,9 +66,13 @@ inline MsgView msg_view(uint8_t *base, int cap) {
 // ---- push exchange: the receive slots of a rank and the two words its neighbours publish into ---------------------------------
 // block = [flag from left, flag from right, pad to 256 B][slot(side 0, parity 0)][slot(0, 1)][slot(1, 0)][slot(1, 1)], a slot is one
 // message (header + arrays for the full halo capacity).  side 0 = written by the left neighbour, side 1 = by the right one.
+// Behind the slots: the push allreduce's landing area, [parity][from rank][P2P_RED_MAX doubles]; its flags are words 16 + rank of
+// the flag region.
 constexpr size_t P2P_FLAGS_BYTES = 256;
+constexpr int P2P_RED_MAX = 96, P2P_MAX_RANKS = 32, P2P_RED_FLAG0 = 16;
 inline size_t p2p_slot_bytes(int cap) { return (msg_bytes(cap) + 255) / 256 * 256; }
-inline size_t p2p_block_bytes(int cap) { return P2P_FLAGS_BYTES + 4 * p2p_slot_bytes(cap); }
+inline size_t p2p_red_offset(int cap) { return P2P_FLAGS_BYTES + 4 * p2p_slot_bytes(cap); }
+inline size_t p2p_block_bytes(int cap, int nranks) { return p2p_red_offset(cap) + (size_t)2 * nranks * P2P_RED_MAX * sizeof(double); }
 inline uint8_t *p2p_slot(uint8_t *block, int cap, int side, int parity) { return block + P2P_FLAGS_BYTES + (size_t)(side * 2 + parity) * p2p_slot_bytes(cap); }
 inline int *p2p_flag(uint8_t *block, int side) { return reinterpret_cast<int *>(block) + side; }
 
@@ -104,6 +108,51 @@ __global__ void k_p2p_wait(const int *flagL, const int *flagR, int seq, int *err
         }
     }
     __threadfence_system();
+}
+
+// Push allreduce (sum of `count` <= P2P_RED_MAX doubles in place, every rank ends with the same bits): one block per rank stores its
+// values into EVERY rank's landing area (its own included), publishes the sequence number in every rank's flag word, waits until
+// all ranks have published theirs here, and adds the contributions in rank order.  One launch and one NVLink round trip instead
+// of the ~45-60 us the 34-double ncclAllReduce of the moment sums took at 8 GPUs (SPHSM_TRACE) — that chain (sums -> allreduce ->
+// solve) is what the gather waits for.  Two landing areas by parity: a rank can be at most one allreduce ahead of the slowest.
+__global__ void __launch_bounds__(128) k_p2p_allreduce(double *totals, int count, int rank, int nranks, int seq, uint8_t *const *__restrict__ blocks,
+                                                       size_t red_off, int *err, unsigned long long timeout_ns) {
+    const int t = threadIdx.x, par = seq & 1;
+    if (t < count) {
+        const double v = totals[t];
+        for (int p = 0; p < nranks; p++) {
+            double *dst = reinterpret_cast<double *>(blocks[p] + red_off) + ((size_t)par * nranks + rank) * P2P_RED_MAX;
+            *reinterpret_cast<volatile double *>(dst + t) = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < nranks) {
+        __threadfence_system();
+        *reinterpret_cast<volatile int *>(reinterpret_cast<int *>(blocks[t]) + P2P_RED_FLAG0 + rank) = seq;
+        const volatile int *f = reinterpret_cast<const int *>(blocks[rank]) + P2P_RED_FLAG0 + t;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
+        while (*f - seq < 0) {
+            if ((++spins & 1023u) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > timeout_ns) {  // a rank that never arrives: the step fails instead of hanging the device
+                    atomicAdd(&err[1], 1);
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t < count) {
+        const volatile double *src = reinterpret_cast<const double *>(blocks[rank] + red_off) + (size_t)par * nranks * P2P_RED_MAX;
+        double sum = 0.0;
+        for (int p = 0; p < nranks; p++) sum += src[(size_t)p * P2P_RED_MAX + t];
+        totals[t] = sum;
+    }
 }
 
 // exchange 2 (pass A's records of a boundary plane) reuses the message buffers: [count, pad x3] [V x cap] [S x cap]

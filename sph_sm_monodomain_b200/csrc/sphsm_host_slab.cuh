@@ -81,65 +81,69 @@ static int comm_alloc(sphsm_handle *h) {
     return SPHSM_OK;
 }
 
-// ---- push exchange set-up: every rank maps its neighbours' receive blocks (CUDA IPC over NVLink); all ranks or none -------------
+// ---- push exchange / push allreduce set-up: every rank maps every other rank's block (CUDA IPC over NVLink); all ranks or none ---
 // (collective: called by every rank from sphsm_comm_init, whatever its own outcome so far)
 static int p2p_setup(sphsm_handle *h) {
-    h->p2p_on = false;
-    if (h->nranks < 2) return SPHSM_OK;
+    h->p2p_on = h->p2p_red_on = false;
+    const int nr = h->nranks;
+    if (nr < 2) return SPHSM_OK;
     const int cap = h->send_cap;
-    const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
-    int ok = g_p2p ? 1 : 0;
-    cudaIpcMemHandle_t hs[3];  // mine, the left neighbour's, the right neighbour's
-    memset(hs, 0, sizeof hs);
-    if (ok && cudaMalloc(&h->p2p_block, p2p_block_bytes(cap)) != cudaSuccess) { ok = 0; h->p2p_block = nullptr; }
+    int ok = (g_p2p && nr <= P2P_MAX_RANKS) ? 1 : 0;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    std::vector<cudaIpcMemHandle_t> hs(nr);
+    memset(hs.data(), 0, hb * nr);
+    if (ok && cudaMalloc(&h->p2p_block, p2p_block_bytes(cap, nr)) != cudaSuccess) { ok = 0; h->p2p_block = nullptr; }
     if (ok) {
-        ok = cudaMemset(h->p2p_block, 0, p2p_block_bytes(cap)) == cudaSuccess && cudaMemset(h->p2p_block, 0xff, P2P_FLAGS_BYTES) == cudaSuccess &&  // flags = -1
-             cudaIpcGetMemHandle(&hs[0], h->p2p_block) == cudaSuccess;
+        ok = cudaMemset(h->p2p_block, 0, p2p_block_bytes(cap, nr)) == cudaSuccess && cudaMemset(h->p2p_block, 0xff, P2P_FLAGS_BYTES) == cudaSuccess &&  // flags = -1
+             cudaIpcGetMemHandle(&hs[h->rank], h->p2p_block) == cudaSuccess;
     }
     cudaGetLastError();
     uint8_t *d_hs = nullptr;
     double *d_ok = nullptr;
-    CU(cudaMalloc(&d_hs, sizeof hs));
-    CU(cudaMalloc(&d_ok, sizeof(double)));
-    CU(cudaMemcpy(d_hs, hs, sizeof hs, cudaMemcpyHostToDevice));
-    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    CU(cudaMalloc(&d_hs, hb * nr));
+    CU(cudaMalloc(&d_ok, 2 * sizeof(double)));
+    CU(cudaMemcpy(d_hs, hs.data(), hb * nr, cudaMemcpyHostToDevice));
     NC(g_nccl.GroupStart());
-    if (has_left) {
-        NC(g_nccl.Send(d_hs, hb, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(d_hs + hb, hb, NCCL_CHAR, h->rank - 1, h->nccl_comm, h->stream));
-    }
-    if (has_right) {
-        NC(g_nccl.Send(d_hs, hb, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
-        NC(g_nccl.Recv(d_hs + 2 * hb, hb, NCCL_CHAR, h->rank + 1, h->nccl_comm, h->stream));
+    for (int p = 0; p < nr; p++) {
+        if (p == h->rank) continue;
+        NC(g_nccl.Send(d_hs + hb * h->rank, hb, NCCL_CHAR, p, h->nccl_comm, h->stream));
+        NC(g_nccl.Recv(d_hs + hb * p, hb, NCCL_CHAR, p, h->nccl_comm, h->stream));
     }
     NC(g_nccl.GroupEnd());
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(hs, d_hs, sizeof hs, cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 2 && ok; k++) {
-        if (!(k == 0 ? has_left : has_right)) continue;
+    CU(cudaMemcpy(hs.data(), d_hs, hb * nr, cudaMemcpyDeviceToHost));
+    h->p2p_all.assign(nr, nullptr);
+    for (int p = 0; p < nr && ok; p++) {
+        if (p == h->rank) { h->p2p_all[p] = h->p2p_block; continue; }
         void *ptr = nullptr;
-        if (cudaIpcOpenMemHandle(&ptr, hs[1 + k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
-        else h->p2p_peer[k] = static_cast<uint8_t *>(ptr);
+        if (cudaIpcOpenMemHandle(&ptr, hs[p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        else h->p2p_all[p] = static_cast<uint8_t *>(ptr);
     }
-    const double mine = ok ? 1.0 : 0.0;
-    double sum = 0.0;
-    CU(cudaMemcpy(d_ok, &mine, sizeof mine, cudaMemcpyHostToDevice));
-    NC(g_nccl.AllReduce(d_ok, d_ok, 1, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm, h->stream));
+    const double mine[2] = {ok ? 1.0 : 0.0, (ok && g_p2p_red) ? 1.0 : 0.0};
+    double sum[2] = {0.0, 0.0};
+    CU(cudaMemcpy(d_ok, mine, sizeof mine, cudaMemcpyHostToDevice));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 2, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(&sum, d_ok, sizeof sum, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sum, d_ok, sizeof sum, cudaMemcpyDeviceToHost));
     cudaFree(d_hs);
     cudaFree(d_ok);
-    if ((int)(sum + 0.5) == h->nranks) {
+    if ((int)(sum[0] + 0.5) == nr) {
         h->p2p_on = true;
+        h->p2p_red_on = (int)(sum[1] + 0.5) == nr;
         h->p2p_slot_bytes = p2p_slot_bytes(cap);
-    } else {  // some rank could not map a neighbour (or runs with SPHSM_P2P=0): everybody stays on ncclSend / ncclRecv
-        for (int k = 0; k < 2; k++)
-            if (h->p2p_peer[k]) { cudaIpcCloseMemHandle(h->p2p_peer[k]); h->p2p_peer[k] = nullptr; }
+        if (h->rank > 0) h->p2p_peer[0] = h->p2p_all[h->rank - 1];
+        if (h->rank < nr - 1) h->p2p_peer[1] = h->p2p_all[h->rank + 1];
+        CU(cudaMalloc(&h->d_p2p_all, nr * sizeof(uint8_t *)));
+        CU(cudaMemcpy(h->d_p2p_all, h->p2p_all.data(), nr * sizeof(uint8_t *), cudaMemcpyHostToDevice));
+    } else {  // some rank could not map a peer (or runs with SPHSM_P2P=0): everybody stays on NCCL
+        for (int p = 0; p < nr; p++)
+            if (h->p2p_all[p] && h->p2p_all[p] != h->p2p_block) cudaIpcCloseMemHandle(h->p2p_all[p]);
+        h->p2p_all.clear();
         if (h->p2p_block) { cudaFree(h->p2p_block); h->p2p_block = nullptr; }
     }
     return SPHSM_OK;
 }
-extern "C" int sphsm_comm_p2p(sphsm_handle *h) { return h && h->p2p_on ? 1 : 0; }
+extern "C" int sphsm_comm_p2p(sphsm_handle *h) { return !h ? 0 : (h->p2p_on ? 1 : 0) | (h->p2p_red_on ? 2 : 0); }
 
 extern "C" int sphsm_comm_unique_id(void *id128) {
     sphsm_handle *h = nullptr;
@@ -329,8 +333,18 @@ extern "C" int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int c
 }
 
 // ---- collectives: NCCL (one process per GPU) --------------------------------------------------------------------
+static unsigned long long p2p_timeout_ns() {
+    static const unsigned long long v =
+        (unsigned long long)(getenv("SPHSM_P2P_TIMEOUT_S") ? std::max(1, atoi(getenv("SPHSM_P2P_TIMEOUT_S"))) : 60) * 1000000000ull;
+    return v;
+}
 static int comm_allreduce(sphsm_handle *h, int count) {
     if (h->comm_mode != 1 || h->nranks == 1) return SPHSM_OK;  // single GPU; the local group sums between phases
+    if (h->p2p_red_on && count <= P2P_RED_MAX) {  // push allreduce: one launch, one NVLink round trip (k_p2p_allreduce)
+        LAUNCH(k_p2p_allreduce, 1, 128, h->totals, count, h->rank, h->nranks, (int)(h->red_seq++), h->d_p2p_all, p2p_red_offset(h->send_cap), h->d_err,
+               p2p_timeout_ns());
+        return SPHSM_OK;
+    }
     NC(g_nccl.AllReduce(h->totals, h->totals, (size_t)count, NCCL_DOUBLE, NCCL_SUM, h->nccl_comm_red, h->launch_stream));
     return SPHSM_OK;
 }
@@ -411,8 +425,7 @@ static int p2p_signal(sphsm_handle *h) {  // (on h->launch_stream, behind the pa
     return SPHSM_OK;
 }
 static int p2p_wait(sphsm_handle *h) {  // (on h->launch_stream, before the unpack)
-    static const unsigned long long timeout_ns =
-        (unsigned long long)(getenv("SPHSM_P2P_TIMEOUT_S") ? std::max(1, atoi(getenv("SPHSM_P2P_TIMEOUT_S"))) : 60) * 1000000000ull;
+    const unsigned long long timeout_ns = p2p_timeout_ns();
     const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
     LAUNCH(k_p2p_wait, 1, 32, has_left ? p2p_flag(h->p2p_block, 0) : nullptr, has_right ? p2p_flag(h->p2p_block, 1) : nullptr, (int)(h->x1_seq - 1), h->d_err,
            timeout_ns);

@@ -293,7 +293,12 @@ class Sim:
 
     def push_exchange(self):
         """True when exchange 1 runs as direct stores into the neighbours' memory (CUDA IPC over NVLink) instead of ncclSend / ncclRecv."""
-        return bool(self.lib.sphsm_comm_p2p(self.h))
+        return bool(self.lib.sphsm_comm_p2p(self.h) & 1)
+
+    def push_allreduce(self):
+        """True when the small allreduces of the slab step (shape-matching moment sums + error flag) run as the one-kernel push allreduce
+        over the same IPC mappings instead of ncclAllReduce."""
+        return bool(self.lib.sphsm_comm_p2p(self.h) & 2)
 
     def x1_sizes(self):
         """Capacities (particles) of the exchange-1 messages packed last: to left, to right, from left, from right."""

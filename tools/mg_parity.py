@@ -132,7 +132,7 @@ if rank == 0:
     print(json.dumps({"mg_parity": "ok" if ok else "FAIL", "ranks": world_size, "particles": n, "steps": a.steps, "quadratic": a.quadratic,
                       "max_rel_dev_vs_single_gpu": err, "owned_per_rank": [int(c.item()) for c in cnts],
                       "every_particle_owned_once": bool((seen == 1).all()), "bit_identical": bool(np.array_equal(got, ref)),
-                      "push_exchange": sim.push_exchange()}), flush=True)
+                      "push_exchange": sim.push_exchange(), "push_allreduce": sim.push_allreduce()}), flush=True)
     rc = 0 if ok else 1
 dist.barrier()
 dist.destroy_process_group()

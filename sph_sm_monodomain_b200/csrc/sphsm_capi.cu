@@ -130,9 +130,9 @@ struct sphsm_handle {
     int alloc_n = 0;          // slots allocated per array (capacity + room for two halo messages in slab mode)
     uint8_t *msg_send[2] = {nullptr, nullptr}, *msg_recv[2] = {nullptr, nullptr};  // [0] left neighbour, [1] right neighbour
     // push exchange (NCCL mode, neighbours reachable through CUDA IPC): exchange 1 is written by the packing kernel straight into the
-    // neighbour's receive slots over NVLink (p2p_push_view), a one-thread kernel publishes count + sequence number, the receiver's
-    // stream polls its own flag word (k_p2p_wait) — no ncclSend / ncclRecv, no host-known message size
-    uint8_t *p2p_block = nullptr;                   // [flags 256 B][from left, parity 0/1][from right, parity 0/1]
+    // neighbour's receive slots over NVLink (x1_send_view), a one-thread kernel publishes count + sequence number, the receiver's
+    // unpack kernel polls its own flag word — no ncclSend / ncclRecv, no host-known message size
+    uint8_t *p2p_block = nullptr;                   // [flags 256 B][from left, parity 0/1][from right, parity 0/1][allreduce landing area]
     uint8_t *p2p_peer[2] = {nullptr, nullptr};      // the neighbours' blocks, mapped here (entries of p2p_all)
     std::vector<uint8_t *> p2p_all;                 // every rank's block (own = p2p_block): the push allreduce stores into all of them
     uint8_t **d_p2p_all = nullptr;                  //   the same table in device memory
@@ -160,7 +160,7 @@ struct sphsm_handle {
     // planes are still being integrated).  Anything that changes particle state other than stimulation values between two steps
     // voids it (x1_early_valid = false): the next step then classifies and exchanges again, on every rank alike — state mutators
     // are collective calls in slab mode.
-    bool x1_early_pending = false, x1_early_valid = false, check_interior_pending = false;
+    bool x1_early_pending = false, x1_early_valid = false, check_interior_pending = false, drop_in_unpack = false;
     cudaEvent_t ev_x1 = nullptr, ev_meta_ready = nullptr;
     cudaStream_t meta_stream = nullptr;  // the 32-byte read-backs of SlabMeta travel beside the step, not inside its main stream
     // exchange-1 messages are sized from the populations both sides of a face saw X1_LAG exchanges ago (see x1_plan)

@@ -87,28 +87,9 @@ __global__ void k_p2p_signal(const int *__restrict__ cntL, const int *__restrict
     if (flagL) *reinterpret_cast<volatile int *>(flagL) = seq;
     if (flagR) *reinterpret_cast<volatile int *>(flagR) = seq;
 }
-// before the unpack (same stream): lane `side` polls this rank's own flag word until the neighbour has published exchange `seq`.
-// A neighbour that never arrives (its process died, or the two sides lost count of the exchanges) ends the wait after
-// `timeout_ns` with err[1] raised, so the step fails like any other exchange error instead of hanging the device.
-__global__ void k_p2p_wait(const int *flagL, const int *flagR, int seq, int *err, unsigned long long timeout_ns) {
-    if (blockIdx.x != 0 || threadIdx.x > 1) return;
-    const int *f = threadIdx.x == 0 ? flagL : flagR;
-    if (!f) return;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    unsigned spins = 0;
-    while (*reinterpret_cast<const volatile int *>(f) - seq < 0) {
-        if ((++spins & 1023u) == 0) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (t - t0 > timeout_ns) {
-                atomicAdd(&err[1], 1);
-                break;
-            }
-        }
-    }
-    __threadfence_system();
-}
+// (the receiver's side is in k_mg_unpack: its blocks poll this rank's own flag words until the neighbours have published exchange
+// `seq`; a neighbour that never arrives — its process died, or the two sides lost count of the exchanges — ends the wait after a
+// time-out with err[1] raised, so the step fails like any other exchange error instead of hanging the device)
 
 // Push allreduce (sum of `count` <= P2P_RED_MAX doubles in place, every rank ends with the same bits): one block per rank stores its
 // values into EVERY rank's landing area (its own included), publishes the sequence number in every rank's flag word, waits until
@@ -238,15 +219,9 @@ __global__ void __launch_bounds__(256) k_mg_classify_rng(const __grid_constant__
         else atomicAdd(&err[1], 1);
     }
 }
-// what is left of k_mg_classify at the start of the next step when its exchange has already happened: last step's halo copies
-// are dropped, and an interior particle that now sits where it should have been sent (it crossed two planes) is an error
-__global__ void __launch_bounds__(256) k_mg_drop_halos(Arrays a, const SlabMeta *__restrict__ m, int cap) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 2 * cap) return;
-    const int side = idx >= cap, k = idx - side * cap;
-    const int first = side ? m->own_end : 0, cnt = side ? m->n_live - m->own_end : m->own_begin;
-    if (k < cnt) a.P[first + k].x = __int_as_float(0x7fc00000);
-}
+// What is left of k_mg_classify at the start of the next step when its exchange has already happened: last step's halo copies are
+// dropped (inside k_mg_unpack), and an interior particle that now sits where it should have been sent (it crossed two planes) is
+// an error
 __global__ void __launch_bounds__(256) k_mg_check_interior(const __grid_constant__ DevParams p, const float4 *__restrict__ P, const SlabMeta *__restrict__ m,
                                                            int has_left, int has_right, int *err) {
     const int s = m->rng_int2[0] + blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,10 +234,41 @@ __global__ void __launch_bounds__(256) k_mg_check_interior(const __grid_constant
 // A message whose header count exceeds the capacity was truncated by its sender: the receiver flags it in the same step.
 // capL / capR: the capacity this exchange's messages were laid out for (<= cap, see x1_plan).  Thread 0 files the populations of the
 // exchange — what this rank sent (its send headers are still intact) and what it received — for the sizing of a later one.
+// Push exchange: flagL / flagR != nullptr make every block poll this rank's flag words until the neighbours have published exchange
+// `seq`, and drop != 0 retires last step's halo copies on the way (both were kernels of their own at first: three launches at the
+// head of the slab step are one).
 __global__ void __launch_bounds__(256) k_mg_unpack(const SlabMeta *__restrict__ prev, Arrays a, int has_left, int has_right, MsgView L, MsgView R,
                                                    int cap, int capL, int capR, int *err, const int *__restrict__ sentL, const int *__restrict__ sentR,
-                                                   int *__restrict__ rec) {
+                                                   int *__restrict__ rec, const int *flagL, const int *flagR, int seq, unsigned long long timeout_ns,
+                                                   int drop) {
+    if (flagL || flagR) {
+        if (threadIdx.x < 2) {
+            const int *f = threadIdx.x == 0 ? flagL : flagR;
+            if (f) {
+                unsigned long long t0;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                unsigned spins = 0;
+                while (*reinterpret_cast<const volatile int *>(f) - seq < 0) {
+                    if ((++spins & 1023u) == 0) {
+                        unsigned long long t;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                        if (t - t0 > timeout_ns) {
+                            if (blockIdx.x == 0) atomicAdd(&err[1], 1);
+                            break;
+                        }
+                    }
+                }
+                __threadfence_system();
+            }
+        }
+        __syncthreads();
+    }
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (drop && idx < 2 * cap) {
+        const int side = idx >= cap, k = idx - side * cap;
+        const int first = side ? prev->own_end : 0, cnt = side ? prev->n_live - prev->own_end : prev->own_begin;
+        if (k < cnt) a.P[first + k].x = __int_as_float(0x7fc00000);
+    }
     if (idx == 0) {
         rec[0] = has_left ? *sentL : 0;
         rec[1] = has_right ? *sentR : 0;

@@ -424,13 +424,6 @@ static int p2p_signal(sphsm_handle *h) {  // (on h->launch_stream, behind the pa
            has_left ? p2p_flag(h->p2p_peer[0], 1) : nullptr, has_right ? p2p_flag(h->p2p_peer[1], 0) : nullptr, q);
     return SPHSM_OK;
 }
-static int p2p_wait(sphsm_handle *h) {  // (on h->launch_stream, before the unpack)
-    const unsigned long long timeout_ns = p2p_timeout_ns();
-    const bool has_left = h->rank > 0, has_right = h->rank < h->nranks - 1;
-    LAUNCH(k_p2p_wait, 1, 32, has_left ? p2p_flag(h->p2p_block, 0) : nullptr, has_right ? p2p_flag(h->p2p_block, 1) : nullptr, (int)(h->x1_seq - 1), h->d_err,
-           timeout_ns);
-    return SPHSM_OK;
-}
 
 // exchange 2: pass A's records of the two boundary planes, packed by k_mg_pack2 into the (free by now) message buffers.  The
 // messages have a fixed size like those of exchange 1 — the plane populations are only known on the device — and carry the
@@ -543,7 +536,7 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 // exchange 1 of this step left at the end of the previous one (phase 5): only the stale halo copies have to go,
                 // and nothing in the interior may sit where it should have been sent from (checked beside the sums)
                 h->x1_early_pending = false;
-                LAUNCH(k_mg_drop_halos, cdiv(2 * cap, 256), 256, h->cur, h->d_meta[h->meta_cur], cap);
+                h->drop_in_unpack = true;  // (k_mg_drop_halos rides in k_mg_unpack)
                 h->check_interior_pending = true;  // (queued behind the allreduce + solve: see mg_check_interior)
                 CU(cudaStreamWaitEvent(h->stream, h->ev_x1, 0));
                 trace_mark(h, "halos dropped, early exchange 1 awaited");
@@ -568,10 +561,13 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 const int slot = (int)((h->x1_seq - 1) % sphsm_handle::X1_RING);  // (its last read-back left X1_RING exchanges ago: a wait for form)
                 const bool record = g_x1_dynamic && !h->p2p_on;  // (only the sized ncclSend / ncclRecv messages need the populations on the host)
                 if (record && h->x1rec_seq[slot] >= 0) CU(cudaStreamWaitEvent(h->stream, h->ev_x1rec[slot], 0));
-                if (h->p2p_on && (rc = p2p_wait(h)) != 0) return rc;  // the neighbours have published this exchange
+                // push exchange: the blocks poll the flag words the neighbours publish this exchange in
+                const int *fl = h->p2p_on && has_left ? p2p_flag(h->p2p_block, 0) : nullptr, *fr = h->p2p_on && has_right ? p2p_flag(h->p2p_block, 1) : nullptr;
                 LAUNCH(k_mg_unpack, cdiv(2 * cap, 256), 256, prev, h->cur, has_left ? 1 : 0, has_right ? 1 : 0, x1_recv_view(h, 0), x1_recv_view(h, 1), cap,
                        h->x1_recv_cap[0], h->x1_recv_cap[1], h->d_err,
-                       (const int *)h->msg_send[0], (const int *)h->msg_send[1], h->d_x1rec + 4 * slot);
+                       (const int *)h->msg_send[0], (const int *)h->msg_send[1], h->d_x1rec + 4 * slot, fl, fr, (int)(h->x1_seq - 1), p2p_timeout_ns(),
+                       h->drop_in_unpack ? 1 : 0);
+                h->drop_in_unpack = false;
                 if (record && (rc = x1_record_launch(h)) != 0) return rc;
             }
             // the entries to sort are the previous live slots + both message regions; the kernels read that count from `prev`,

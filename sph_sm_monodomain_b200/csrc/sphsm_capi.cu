@@ -394,6 +394,9 @@ static int setup_grid_buffers(sphsm_handle *h) {
     while ((1ll << bits) < (long long)h->dp.num_cells + 1) bits++;
     h->sort_passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
     if (h->sort_passes > MAX_SORT_PASSES) return fail(h, SPHSM_ERR_INVALID, "grid too large for the radix sort key");
+    // the memsets above run in the legacy default stream, which the handle's non-blocking streams do not wait for: without this the
+    // first scan after sphsm_comm_set_slab could meet a not-yet-cleared epoch / state table (seen once as a spurious exchange error)
+    CU(cudaDeviceSynchronize());
     return SPHSM_OK;
 }
 

@@ -78,6 +78,7 @@ static int comm_alloc(sphsm_handle *h) {
     h->x1_send_cap[0] = h->x1_send_cap[1] = h->x1_recv_cap[0] = h->x1_recv_cap[1] = cap;
     CU(cudaMallocHost(&h->h_ring, sphsm_handle::META_RING * 8 * sizeof(int)));
     for (auto &e : h->ev_ring) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaDeviceSynchronize());  // (legacy-stream memsets above: the handle's non-blocking streams do not wait for them)
     return SPHSM_OK;
 }
 
@@ -97,6 +98,7 @@ static int p2p_setup(sphsm_handle *h) {
         ok = cudaMemset(h->p2p_block, 0, p2p_block_bytes(cap, nr)) == cudaSuccess && cudaMemset(h->p2p_block, 0xff, P2P_FLAGS_BYTES) == cudaSuccess &&  // flags = -1
              cudaIpcGetMemHandle(&hs[h->rank], h->p2p_block) == cudaSuccess;
     }
+    cudaDeviceSynchronize();  // (the memsets ran in the legacy stream; peers may store into this block as soon as they have mapped it)
     cudaGetLastError();
     uint8_t *d_hs = nullptr;
     double *d_ok = nullptr;

@@ -19,5 +19,4 @@ import sys,json
 for ln in sys.stdin:
     d=json.loads(ln); print({k:d[k] for k in ('value','ms_per_step','n_gpus','gpu_launches')}, 'e2e', d['e2e']['value'], d['roofline']['whole_step'])
 "
-SPHSM_TRACE=450 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 bench.py --gpus 8 --steps 100 --warmup 5 --no-cpu-baseline > gpurun_out/trace8.log 2> gpurun_out/trace8.err; echo "trace exit $?"
 fi

@@ -40,9 +40,9 @@ def launches(nsteps=3):
         lines = [ln for ln in fh if not ln.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"].split("(")[0] for r in rows]
-    # a step starts at its first sort kernel: k_cell_count / k_scan_tile_sums (counting sort), or the first radix pass (k_hash before it);
+    # a step starts at its first sort kernel: k_cell_count / k_scan_onepass (k_scan_tile_sums before round 2's single-pass scan), or the first radix pass (k_hash before it);
     # with the moment sums forked onto the side stream, k_moments / k_sum_partials_par may be listed just before it
-    starts = [i for i, n in enumerate(names) if "k_scan_tile_sums" in n]
+    starts = [i for i, n in enumerate(names) if "k_scan_tile_sums" in n or "k_scan_onepass" in n]
     starts = [i - 1 if i > 0 and "k_cell_count" in names[i - 1] else i for i in starts]  # (pass B files the counts on one GPU)
     if not starts:
         starts = [i for i, n in enumerate(names) if "k_radix_pass" in n and (i == 0 or "k_radix_pass" not in names[i - 1])]

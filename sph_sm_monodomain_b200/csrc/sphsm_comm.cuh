@@ -10,11 +10,12 @@
 //   exchange 1      messages with the count in the header.  NCCL mode with CUDA-IPC neighbours: the packing kernel stores them
 //                   straight into the neighbour's receive slot over NVLink and a flag word publishes them (push exchange, below);
 //                   otherwise ncclSend / ncclRecv of the full capacity (or of a lagged estimate, x1_plan)
-//   k_mg_unpack     arrivals are appended behind the local particles; unused message slots become dead entries that the
-//                   sort pushes into the limbo bucket
+//   k_mg_unpack     (push exchange: waits for the neighbours' flag words, retires last step's halo copies) arrivals are appended
+//                   behind the local particles; unused message slots become dead entries that the sort pushes into the limbo bucket
 //   ... hash, sort (canonical in-cell order = ascending original index, so both sides of a slab face hold that plane in
 //       the same order), cell table; k_mg_meta + one 32-byte read-back give the host the plane boundaries ...
-//   exchange 2      after pass A the boundary planes' V / S records travel as contiguous slot ranges
+//   exchange 2      after pass A the boundary planes' V / S records travel as contiguous slot ranges (ncclSend / ncclRecv)
+//   k_p2p_allreduce the moment sums + error flag of the step, summed over the ranks through the same peer mappings
 #pragma once
 #include <limits.h>
 #include <stddef.h>

@@ -521,8 +521,9 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 CU(cudaEventRecord(h->ev_fork, h->stream));
                 CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
                 h->launch_stream = h->side_stream;
-                // (NCCL runs one communicator's operations in issue order whatever their streams: the allreduce is issued
-                // after exchange 1, in mg_forked_allreduce, so that the exchange does not queue behind the sums)
+                // (the NCCL form of the allreduce is issued after exchange 1, in mg_forked_allreduce: NCCL runs one communicator's
+                // operations in issue order whatever their streams, and the exchange must not queue behind the sums; the push
+                // allreduce has no such order, it simply takes the same place)
                 rc = moments_part(h);
                 h->launch_stream = h->stream;
                 if (rc) return rc;
@@ -538,10 +539,10 @@ static int mg_phase(sphsm_handle *h, int phase, int *coll, int *count) {
                 // exchange 1 of this step left at the end of the previous one (phase 5): only the stale halo copies have to go,
                 // and nothing in the interior may sit where it should have been sent from (checked beside the sums)
                 h->x1_early_pending = false;
-                h->drop_in_unpack = true;  // (k_mg_drop_halos rides in k_mg_unpack)
+                h->drop_in_unpack = true;  // (k_mg_unpack retires them on its way)
                 h->check_interior_pending = true;  // (queued behind the allreduce + solve: see mg_check_interior)
                 CU(cudaStreamWaitEvent(h->stream, h->ev_x1, 0));
-                trace_mark(h, "halos dropped, early exchange 1 awaited");
+                trace_mark(h, "early exchange 1 awaited");
                 if (h->gt) h->gt->end_group(KG_OTHER);
                 *coll = COLL_EXCH1_TAKEN;
                 return SPHSM_OK;

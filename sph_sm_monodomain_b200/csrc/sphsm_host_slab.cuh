@@ -337,7 +337,7 @@ extern "C" int sphsm_download_owned(sphsm_handle *h, int *ids, float *xyz, int c
 // ---- collectives: NCCL (one process per GPU) --------------------------------------------------------------------
 static unsigned long long p2p_timeout_ns() {
     static const unsigned long long v =
-        (unsigned long long)(getenv("SPHSM_P2P_TIMEOUT_S") ? std::max(1, atoi(getenv("SPHSM_P2P_TIMEOUT_S"))) : 60) * 1000000000ull;
+        (unsigned long long)(getenv("SPHSM_P2P_TIMEOUT_S") ? std::max(1, atoi(getenv("SPHSM_P2P_TIMEOUT_S"))) : 120) * 1000000000ull;
     return v;
 }
 static int comm_allreduce(sphsm_handle *h, int count) {
